@@ -1,0 +1,429 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * W[N,K]^T     16-bit operands (bf16 or fp16), fp32 accumulate in TMEM
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane,
+// also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> fused math -> HBM).
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop
+// of tile i+1.  A-operand tiles come either from a 2-D tensor map (linear layers) or from a
+// 4-D NHWC tensor map walked over the 9 filter taps (3x3 convolution as implicit GEMM; the
+// zero padding is TMA's out-of-bounds fill, negative coordinates included).
+//
+// Reference call sites replaced: see include/rfb200.h (rfb_gemm).
+#include <atomic>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace rfb {
+
+std::atomic<long long> g_launch_count{0};
+
+struct GemmKParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_kb;
+  int a_mode;
+  int H, Wd, Cin, tw, th, tiles_x, tiles_y, kb_per_tap;
+  uint32_t idesc;
+  int epi;
+  const float* bias;
+  const void* res1;
+  const void* res2;
+  int res_dtype;
+  long long ldres;
+  void* out;
+  int out_dtype;
+  long long ldo;
+  void* out_act;
+  const int* row_map;
+  const float* w2;
+  const float* b2;
+  int n_store;
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr uint32_t kABytes = kBM * kBK * 2;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr uint32_t kSmemBytes = kStages * (kABytes + kBBytes) + 1024 + 256;
+};
+
+__device__ __forceinline__ void load8(const void* base, int dtype, long long idx, float (&x)[8]) {
+  if (dtype == RFB_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    float4 a = p[0], b = p[1];
+    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+  } else {
+    uint4 u = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + idx);
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == RFB_BF16) {
+        x[2 * i] = __uint_as_float(w[i] << 16);
+        x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      } else {
+        __half2 h = *reinterpret_cast<__half2*>(&w[i]);
+        float2 f = __half22float2(h);
+        x[2 * i] = f.x, x[2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(void* base, int dtype, long long idx, const float (&x)[8]) {
+  if (dtype == RFB_F32) {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + idx);
+    p[0] = make_float4(x[0], x[1], x[2], x[3]);
+    p[1] = make_float4(x[4], x[5], x[6], x[7]);
+  } else {
+    uint4 u;
+    if (dtype == RFB_BF16) {
+      u.x = pack_bf16(x[0], x[1]), u.y = pack_bf16(x[2], x[3]);
+      u.z = pack_bf16(x[4], x[5]), u.w = pack_bf16(x[6], x[7]);
+    } else {
+      u.x = pack_f16(x[0], x[1]), u.y = pack_f16(x[2], x[3]);
+      u.z = pack_f16(x[4], x[5]), u.w = pack_f16(x[6], x[7]);
+    }
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + idx) = u;
+  }
+}
+
+// One thread owns one output row; v = 32 consecutive accumulator columns starting at n0.
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long orow, int n0,
+                                               const uint32_t (&v)[32]) {
+  if (p.epi == RFB_EPI_STORE) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n0 + g * 8;
+      if (n >= p.n_store) break;
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+      if (p.bias) {
+        float b[8];
+        load8(p.bias, RFB_F32, n, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += b[j];
+      }
+      if (p.res1) {
+        float r[8];
+        load8(p.res1, p.res_dtype, orow * p.ldres + n, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += r[j];
+      }
+      if (p.res2) {
+        float r[8];
+        load8(p.res2, p.res_dtype, orow * p.ldres + n, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += r[j];
+      }
+      if (p.out) store8(p.out, p.out_dtype, orow * p.ldo + n, x);
+      if (p.out_act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+        store8(p.out_act, p.out_dtype, orow * p.ldo + n, x);
+      }
+    }
+  } else if (p.epi == RFB_EPI_SWIGLU) {
+    if (n0 >= p.N) return;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gate = __uint_as_float(v[g * 8 + j]);
+        const float up = __uint_as_float(v[16 + g * 8 + j]);
+        h[j] = silu_f(gate) * up;
+      }
+      store8(p.out, p.out_dtype, orow * p.ldo + (n0 >> 1) + g * 8, h);
+    }
+  } else {  // RFB_EPI_FINAL (N == 32, n0 == 0)
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = silu_f(__uint_as_float(v[j]) + __ldg(p.bias + j));
+    float* o = static_cast<float*>(p.out) + orow * p.ldo;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float y = __ldg(p.b2 + c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y = fmaf(__ldg(p.w2 + c * 32 + j), h[j], y);
+      y = y > 0.f ? y : 1e-3f * expm1f(y);  // ELU(alpha=1e-3)  view_transformer.py:86,122
+      o[c] = exp10f(y) - 1.0f;              // rendering_pipeline.py:122-123
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr uint32_t B_BYTES = Cfg::kBBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        int m0 = mt * kBM, bi = 0, y0 = 0, x0 = 0;
+        if (p.a_mode == RFB_A_CONV3X3) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          bi = mt / per_img;
+          const int r = mt % per_img;
+          y0 = (r / p.tiles_x) * p.th;
+          x0 = (r % p.tiles_x) * p.tw;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kABytes + B_BYTES);
+          int kw;  // K coordinate in the weight matrix
+          if (p.a_mode == RFB_A_LINEAR) {
+            kw = kb * kBK;
+            tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kw, m0);
+          } else {
+            const int tap = kb / p.kb_per_tap;
+            const int cb = kb % p.kb_per_tap;
+            kw = tap * p.Cin + cb * kBK;
+            tma_load_4d(sA + stage * kABytes, &tmA, &full[stage], cb * kBK, x0 + tap % 3 - 1,
+                        y0 + tap / 3 - 1, bi);
+          }
+          tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], kw, n0);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytes));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int mt = tile / p.num_n_tiles;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      long long orow;
+      bool valid;
+      if (p.a_mode == RFB_A_LINEAR) {
+        const int m = mt * kBM + r;
+        valid = m < p.M;
+        orow = valid ? (p.row_map ? p.row_map[m] : m) : 0;
+      } else {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int bi = mt / per_img;
+        const int rr = mt % per_img;
+        const int y = (rr / p.tiles_x) * p.th + r / p.tw;
+        const int x = (rr % p.tiles_x) * p.tw + r % p.tw;
+        valid = (y < p.H) && (x < p.Wd);
+        orow = (static_cast<long long>(bi) * p.H + y) * p.Wd + x;
+      }
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
+        tmem_wait_ld();
+        if (valid) epilogue_chunk(p, orow, n0 + c * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                       int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::kSmemBytes) != cudaSuccess)
+      return RFB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  g_launch_count++;
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace rfb
+
+using namespace rfb;
+
+extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a || !a->A || !a->W || a->M <= 0 || a->N <= 0 || a->K <= 0) return RFB_ERR_ARG;
+  if (a->dtype != RFB_BF16 && a->dtype != RFB_F16) return RFB_ERR_ARG;
+
+  GemmKParams p{};
+  p.M = a->M, p.N = a->N, p.K = a->K;
+  p.a_mode = a->a_mode;
+  p.epi = a->epi;
+  p.bias = a->bias, p.res1 = a->res1, p.res2 = a->res2, p.res_dtype = a->res_dtype;
+  p.ldres = a->ldres, p.out = a->out, p.out_dtype = a->out_dtype, p.ldo = a->ldo;
+  p.out_act = a->out_act, p.row_map = a->row_map, p.w2 = a->w2, p.b2 = a->b2;
+
+  int bn = a->bn_override;
+  if (bn == 0) {
+    if (a->N <= 32) bn = 32;
+    else if (a->N <= 64) bn = 64;
+    else if (a->N % 256 == 0) bn = 256;
+    else bn = 128;
+  }
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RFB_ERR_ARG;
+
+  if (a->epi == RFB_EPI_STORE) {
+    p.n_store = (a->N + 7) & ~7;
+    if (p.n_store > a->ldo) return RFB_ERR_ARG;
+    if ((a->bias || a->res1 || a->res2) && (a->N % 8) != 0) return RFB_ERR_ARG;
+    if (!a->out && !a->out_act) return RFB_ERR_ARG;
+    const int align = (a->out_dtype == RFB_F32) ? 4 : 8;
+    if (a->ldo % align) return RFB_ERR_ALIGN;
+    if ((a->res1 || a->res2) && a->ldres % ((a->res_dtype == RFB_F32) ? 4 : 8)) return RFB_ERR_ALIGN;
+  } else if (a->epi == RFB_EPI_SWIGLU) {
+    if (a->N % 32 || !a->out || a->out_dtype == RFB_F32 || a->ldo % 8) return RFB_ERR_ARG;
+    p.n_store = a->N;
+  } else if (a->epi == RFB_EPI_FINAL) {
+    if (a->N != 32 || !a->out || !a->bias || !a->w2 || !a->b2) return RFB_ERR_ARG;
+    bn = 32;
+    p.n_store = 32;
+  } else {
+    return RFB_ERR_ARG;
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a->a_mode == RFB_A_LINEAR) {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kBM};
+    if ((rc = make_tmap_16b(&tmA, a->dtype, a->A, 2, dims, strides, box)) != RFB_OK) return rc;
+    p.num_m_tiles = (a->M + kBM - 1) / kBM;
+    p.num_kb = (a->K + kBK - 1) / kBK;
+  } else if (a->a_mode == RFB_A_CONV3X3) {
+    if (a->B <= 0 || a->H <= 0 || a->Wd <= 0 || a->Cin <= 0 || a->K != 9 * a->Cin ||
+        a->M != a->B * a->H * a->Wd || a->row_map)
+      return RFB_ERR_ARG;
+    p.H = a->H, p.Wd = a->Wd, p.Cin = a->Cin;
+    p.tw = (a->Wd >= 16) ? 16 : 8;
+    p.th = kBM / p.tw;
+    p.tiles_x = (a->Wd + p.tw - 1) / p.tw;
+    p.tiles_y = (a->H + p.th - 1) / p.th;
+    p.kb_per_tap = (a->Cin + kBK - 1) / kBK;
+    uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->B};
+    uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->Wd * a->Cin * 2,
+                           (uint64_t)a->H * a->Wd * a->Cin * 2};
+    uint32_t box[4] = {(uint32_t)kBK, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    if ((rc = make_tmap_16b(&tmA, a->dtype, a->A, 4, dims, strides, box)) != RFB_OK) return rc;
+    p.num_m_tiles = a->B * p.tiles_x * p.tiles_y;
+    p.num_kb = 9 * p.kb_per_tap;
+  } else {
+    return RFB_ERR_ARG;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
+    if ((rc = make_tmap_16b(&tmB, a->dtype, a->W, 2, dims, strides, box)) != RFB_OK) return rc;
+  }
+  p.num_n_tiles = (a->N + bn - 1) / bn;
+  p.idesc = umma_idesc_f16(a->dtype == RFB_BF16 ? 1u : 0u, kBM, bn);
+
+  const long long total = (long long)p.num_m_tiles * p.num_n_tiles;
+  int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  int grid = (int)(total < cap ? total : cap);
+
+  switch (bn) {
+    case 32: return launch_gemm<32>(tmA, tmB, p, grid, stream);
+    case 64: return launch_gemm<64>(tmA, tmB, p, grid, stream);
+    case 128: return launch_gemm<128>(tmA, tmB, p, grid, stream);
+    default: return launch_gemm<256>(tmA, tmB, p, grid, stream);
+  }
+}
+
+extern "C" int rfb_version(void) { return 100; }
+extern "C" long long rfb_launch_count(void) { return g_launch_count.load(); }

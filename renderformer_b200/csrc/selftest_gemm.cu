@@ -1,0 +1,275 @@
+// Standalone GPU self-test + micro-benchmark of rfb_gemm (no torch).
+// Checks every epilogue / A-operand mode against a naive CUDA-core reference kernel.
+#include <string.h>
+
+#include "selftest_common.h"
+
+__global__ void ref_linear(const uint16_t* A, long long lda, const uint16_t* W, long long ldw,
+                           float* acc, int M, int N, int K, int bf16) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    uint16_t a = A[m * lda + k], w = W[n * ldw + k];
+    float fa, fw;
+    if (bf16) {
+      fa = __uint_as_float((uint32_t)a << 16), fw = __uint_as_float((uint32_t)w << 16);
+    } else {
+      fa = __half2float(*reinterpret_cast<__half*>(&a));
+      fw = __half2float(*reinterpret_cast<__half*>(&w));
+    }
+    s = fmaf(fa, fw, s);
+  }
+  acc[(long long)m * N + n] = s;
+}
+
+__global__ void ref_conv3(const uint16_t* X, const uint16_t* W, float* acc, int B, int H, int Wd,
+                          int Cin, int Cout, int bf16) {
+  int co = blockIdx.x * blockDim.x + threadIdx.x;
+  long long pix = blockIdx.y;
+  if (co >= Cout) return;
+  int x = pix % Wd, y = (pix / Wd) % H, b = pix / ((long long)Wd * H);
+  float s = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= Wd) continue;
+    const uint16_t* xp = X + (((long long)b * H + yy) * Wd + xx) * Cin;
+    const uint16_t* wp = W + (long long)co * 9 * Cin + (long long)tap * Cin;
+    for (int c = 0; c < Cin; ++c) {
+      uint16_t a = xp[c], w = wp[c];
+      float fa, fw;
+      if (bf16) {
+        fa = __uint_as_float((uint32_t)a << 16), fw = __uint_as_float((uint32_t)w << 16);
+      } else {
+        fa = __half2float(*reinterpret_cast<__half*>(&a));
+        fw = __half2float(*reinterpret_cast<__half*>(&w));
+      }
+      s = fmaf(fa, fw, s);
+    }
+  }
+  acc[pix * Cout + co] = s;
+}
+
+static float silu_h(float x) { return x / (1.0f + expf(-x)); }
+
+struct Case {
+  const char* name;
+  int M, N, K, dtype, a_mode, B, H, Wd, Cin, epi, out_dtype;
+  bool bias, res1, res2, act, rowmap;
+  int res_dtype, bn;
+};
+
+static std::vector<float> to_float(const void* dev, size_t n, int dtype) {
+  std::vector<float> out(n);
+  if (dtype == RFB_F32) {
+    CK(cudaMemcpy(out.data(), dev, n * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint16_t> h(n);
+    CK(cudaMemcpy(h.data(), dev, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) out[i] = h162f(h[i], dtype);
+  }
+  return out;
+}
+
+static void run_case(const Case& c) {
+  const int M = c.M, N = c.N, K = c.K;
+  const long long lda = (c.a_mode == RFB_A_LINEAR) ? K : c.Cin;
+  size_t a_elems = (c.a_mode == RFB_A_LINEAR) ? (size_t)M * K : (size_t)c.B * c.H * c.Wd * c.Cin;
+  std::vector<uint16_t> hA = rand16(a_elems, 11, 1.0f, c.dtype);
+  std::vector<uint16_t> hW = rand16((size_t)N * K, 22, 0.05f, c.dtype);
+  DevBuf<uint16_t> dA(a_elems), dW((size_t)N * K);
+  dA.up(hA), dW.up(hW);
+  DevBuf<float> dacc((size_t)M * N);
+  if (c.a_mode == RFB_A_LINEAR) {
+    dim3 g((N + 127) / 128, M);
+    ref_linear<<<g, 128>>>(dA.p, lda, dW.p, K, dacc.p, M, N, K, c.dtype == RFB_BF16);
+  } else {
+    dim3 g((N + 63) / 64, M);
+    ref_conv3<<<g, 64>>>(dA.p, dW.p, dacc.p, c.B, c.H, c.Wd, c.Cin, N, c.dtype == RFB_BF16);
+  }
+  CK(cudaDeviceSynchronize());
+  std::vector<float> acc = dacc.down();
+
+  // epilogue inputs
+  std::vector<float> hbias = rand32(N, 33, 0.5f);
+  DevBuf<float> dbias(N);
+  dbias.up(hbias);
+  const int out_cols = (c.epi == RFB_EPI_SWIGLU) ? N / 2 : (c.epi == RFB_EPI_FINAL ? 3 : N);
+  const long long ldo = (c.epi == RFB_EPI_STORE) ? ((out_cols + 7) & ~7) : out_cols;
+  const int out_rows = M + (c.rowmap ? 64 : 0);  // row_map scatters into a larger buffer
+  std::vector<int> hmap(M);
+  for (int m = 0; m < M; ++m) hmap[m] = c.rowmap ? (int)(((long long)m * 7919) % M) + 64 * ((m % 2)) : m;
+  if (c.rowmap) {  // make it a true permutation of [0,M) shifted by 13
+    for (int m = 0; m < M; ++m) hmap[m] = (int)((m + 13) % M);
+  }
+  DevBuf<int> dmap(M);
+  dmap.up(hmap);
+  const size_t res_n = (size_t)out_rows * ldo;
+  std::vector<float> hres1f, hres2f;
+  std::vector<float> r1 = rand32(res_n, 44, 1.0f), r2 = rand32(res_n, 55, 1.0f);
+  DevBuf<float> dres1f(res_n), dres2f(res_n);
+  DevBuf<uint16_t> dres1h(res_n), dres2h(res_n);
+  if (c.res_dtype == RFB_F32) {
+    dres1f.up(r1), dres2f.up(r2);
+  } else {
+    std::vector<uint16_t> h1(res_n), h2(res_n);
+    for (size_t i = 0; i < res_n; ++i) {
+      h1[i] = f2h16(r1[i], c.res_dtype), r1[i] = h162f(h1[i], c.res_dtype);
+      h2[i] = f2h16(r2[i], c.res_dtype), r2[i] = h162f(h2[i], c.res_dtype);
+    }
+    dres1h.up(h1), dres2h.up(h2);
+  }
+  std::vector<float> hw2 = rand32(96, 66, 0.3f), hb2 = rand32(3, 77, 0.2f);
+  DevBuf<float> dw2(96), db2(3);
+  dw2.up(hw2), db2.up(hb2);
+
+  const size_t out_n = (size_t)out_rows * ldo;
+  const int osz = (c.out_dtype == RFB_F32) ? 4 : 2;
+  DevBuf<uint8_t> dout(out_n * osz), dact(out_n * osz);
+  dout.fill_byte(0), dact.fill_byte(0);
+
+  rfb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = lda, a.W = dW.p, a.ldw = K, a.dtype = c.dtype;
+  a.a_mode = c.a_mode, a.B = c.B, a.H = c.H, a.Wd = c.Wd, a.Cin = c.Cin, a.epi = c.epi;
+  a.bias = (c.bias || c.epi == RFB_EPI_FINAL) ? dbias.p : nullptr;
+  a.res_dtype = c.res_dtype, a.ldres = ldo;
+  if (c.res1) a.res1 = (c.res_dtype == RFB_F32) ? (void*)dres1f.p : (void*)dres1h.p;
+  if (c.res2) a.res2 = (c.res_dtype == RFB_F32) ? (void*)dres2f.p : (void*)dres2h.p;
+  a.out = dout.p, a.out_dtype = c.out_dtype, a.ldo = ldo;
+  a.out_act = c.act ? dact.p : nullptr;
+  a.row_map = c.rowmap ? dmap.p : nullptr;
+  a.w2 = dw2.p, a.b2 = db2.p, a.bn_override = c.bn;
+  int rc = rfb_gemm(&a, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc != RFB_OK || e != cudaSuccess) {
+    printf("[FAIL] %-46s rc=%d cuda=%s\n", c.name, rc, cudaGetErrorString(e));
+    g_fail++;
+    if (e != cudaSuccess) exit(3);  // context is gone
+    return;
+  }
+  std::vector<float> got = to_float(dout.p, out_n, c.out_dtype);
+  std::vector<float> got_act = to_float(dact.p, out_n, c.out_dtype);
+
+  // expected
+  std::vector<float> exp(out_n, 0.f), exp_act(out_n, 0.f);
+  for (int m = 0; m < M; ++m) {
+    const long long orow = hmap[m];
+    if (c.epi == RFB_EPI_STORE) {
+      for (int n = 0; n < N; ++n) {
+        float v = acc[(size_t)m * N + n];
+        if (c.bias) v += hbias[n];
+        if (c.res1) v += r1[orow * ldo + n];
+        if (c.res2) v += r2[orow * ldo + n];
+        exp[orow * ldo + n] = v;
+        exp_act[orow * ldo + n] = silu_h(v);
+      }
+    } else if (c.epi == RFB_EPI_SWIGLU) {
+      for (int n = 0; n < N; n += 32)
+        for (int j = 0; j < 16; ++j)
+          exp[orow * ldo + n / 2 + j] =
+              silu_h(acc[(size_t)m * N + n + j]) * acc[(size_t)m * N + n + 16 + j];
+    } else {
+      for (int ch = 0; ch < 3; ++ch) {
+        float y = hb2[ch];
+        for (int j = 0; j < 32; ++j) y += hw2[ch * 32 + j] * silu_h(acc[(size_t)m * N + j] + hbias[j]);
+        y = y > 0 ? y : 1e-3f * expm1f(y);
+        exp[orow * 3 + ch] = powf(10.f, y) - 1.f;
+      }
+    }
+  }
+  const double rt = (c.out_dtype == RFB_F32) ? 2e-3 : 1.2e-2;
+  const double at = (c.out_dtype == RFB_F32) ? 2e-3 : 2e-2;
+  report(c.name, got, exp, at, rt, (int)ldo);
+  if (c.act) {
+    std::string nm = std::string(c.name) + " [act]";
+    report(nm.c_str(), got_act, exp_act, at, rt, (int)ldo);
+  }
+}
+
+static void bench(const char* name, int M, int N, int K, int epi, int out_dtype, int bn, int conv_hw = 0,
+                  int Cin = 0, int batch = 1) {
+  const int dtype = conv_hw ? RFB_F16 : RFB_BF16;
+  size_t a_elems = conv_hw ? (size_t)batch * conv_hw * conv_hw * Cin : (size_t)M * K;
+  DevBuf<uint16_t> dA(a_elems), dW((size_t)N * K);
+  CK(cudaMemset(dA.p, 0x3c, a_elems * 2));  // small finite values
+  CK(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2));
+  const int out_cols = (epi == RFB_EPI_SWIGLU) ? N / 2 : N;
+  DevBuf<uint8_t> dout((size_t)M * out_cols * 4);
+  DevBuf<float> dres((size_t)M * out_cols);
+  dres.zero();
+  rfb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = conv_hw ? Cin : K, a.W = dW.p, a.ldw = K;
+  a.dtype = dtype, a.epi = epi, a.out = dout.p, a.out_dtype = out_dtype, a.ldo = out_cols;
+  a.bn_override = bn;
+  if (conv_hw) a.a_mode = RFB_A_CONV3X3, a.B = batch, a.H = conv_hw, a.Wd = conv_hw, a.Cin = Cin;
+  if (epi == RFB_EPI_STORE && out_dtype == RFB_F32 && !conv_hw)
+    a.res1 = dres.p, a.res_dtype = RFB_F32, a.ldres = out_cols;  // residual-stream style
+  for (int i = 0; i < 3; ++i) {
+    int rc = rfb_gemm(&a, 0);
+    if (rc) {
+      printf("bench %s rc=%d\n", name, rc);
+      return;
+    }
+  }
+  CK(cudaDeviceSynchronize());
+  GpuTimer t;
+  const int iters = 20;
+  t.start();
+  for (int i = 0; i < iters; ++i) rfb_gemm(&a, 0);
+  float ms = t.stop() / iters;
+  CK(cudaDeviceSynchronize());
+  double tf = 2.0 * M * (double)N * K / (ms * 1e-3) / 1e12;
+  printf("[BENCH] %-40s M=%d N=%d K=%d bn=%d  %.3f ms  %.1f TFLOP/s\n", name, M, N, K, bn, ms, tf);
+  fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+  const bool do_bench = argc > 1 && !strcmp(argv[1], "bench");
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  printf("rfb version %d\n", rfb_version());
+  if (!do_bench) {
+    const int L = RFB_A_LINEAR, C3 = RFB_A_CONV3X3;
+    std::vector<Case> cases = {
+        // name, M,N,K, dtype, a_mode, B,H,W,Cin, epi, out_dtype, bias,res1,res2,act,rowmap, res_dtype, bn
+        {"linear bf16 128x128x64 f32 (1 tile,1 kb)", 128, 128, 64, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 0, 0, 0, 0, 0, RFB_F32, 128},
+        {"linear bf16 128x128x256 f32 (k loop)", 128, 128, 256, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 0, 0, 0, 0, 0, RFB_F32, 128},
+        {"linear bf16 256x512x1024 f32 bn256", 256, 512, 1024, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 0, 0, 0, 0, 0, RFB_F32, 256},
+        {"linear bf16 300x96x192 ragged bn128", 300, 96, 192, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 0, 0, 0, 0, 0, RFB_F32, 0},
+        {"linear bf16 1040x1024 x1024 Nt-tail out", 1024, 1040, 1024, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_BF16, 0, 0, 0, 0, 0, RFB_F32, 0},
+        {"linear bf16 4112x3072x1024 bf16 bn256", 4112, 3072, 1024, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_BF16, 0, 0, 0, 0, 0, RFB_F32, 256},
+        {"linear bf16 bias+res f32 4112x1024x1024", 4112, 1024, 1024, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 1, 1, 0, 0, 0, RFB_F32, 0},
+        {"linear bf16 res+rowmap f32 2048x1024x512", 2048, 1024, 512, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 0, 1, 0, 0, 1, RFB_F32, 0},
+        {"linear bf16 swiglu 1000x2048x512", 1000, 2048, 512, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_SWIGLU, RFB_BF16, 0, 0, 0, 0, 0, RFB_F32, 0},
+        {"linear f16 bias act f16 4096x256x1024", 4096, 256, 1024, RFB_F16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 1, 0, RFB_F16, 0},
+        {"linear bf16 K=117->128 pad 512x256x128", 512, 256, 128, RFB_BF16, L, 0, 0, 0, 0, RFB_EPI_STORE, RFB_F32, 1, 0, 0, 0, 0, RFB_F32, 0},
+        {"conv3x3 f16 2x32x32 128->128", 2 * 32 * 32, 128, 9 * 128, RFB_F16, C3, 2, 32, 32, 128, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 f16 1x16x16 256->128 res2 act", 256, 128, 9 * 256, RFB_F16, C3, 1, 16, 16, 256, RFB_EPI_STORE, RFB_F16, 1, 1, 1, 1, 0, RFB_F16, 0},
+        {"conv3x3 f16 3x8x8 128->128 (W<16)", 3 * 64, 128, 9 * 128, RFB_F16, C3, 3, 8, 8, 128, RFB_EPI_STORE, RFB_F16, 0, 0, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 f16 1x20x24 96->64 ragged", 480, 64, 9 * 96, RFB_F16, C3, 1, 20, 24, 96, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 f16 1x64x64 128->64 bn64", 4096, 64, 9 * 128, RFB_F16, C3, 1, 64, 64, 128, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 f16 final 1x64x64 64->32->3", 4096, 32, 9 * 64, RFB_F16, C3, 1, 64, 64, 64, RFB_EPI_FINAL, RFB_F32, 1, 0, 0, 0, 0, RFB_F16, 0},
+    };
+    int n = quick ? 3 : (int)cases.size();
+    for (int i = 0; i < n; ++i) run_case(cases[i]);
+    printf("selftest_gemm: %d failure(s)\n", g_fail);
+    if (g_fail) return 1;
+  }
+  if (do_bench || argc == 1) {
+    for (int bn : {256, 128}) {
+      bench("enc qkv        ", 4112, 3072, 1024, RFB_EPI_STORE, RFB_BF16, bn);
+      bench("enc out_proj+res", 4112, 1024, 1024, RFB_EPI_STORE, RFB_F32, bn);
+      bench("enc w13 swiglu ", 4112, 8192, 1024, RFB_EPI_SWIGLU, RFB_BF16, bn);
+      bench("enc w2+res     ", 4112, 1024, 4096, RFB_EPI_STORE, RFB_F32, bn);
+      bench("dec 8v w13     ", 32768, 8192, 1024, RFB_EPI_SWIGLU, RFB_BF16, bn);
+      bench("dec 8v w2+res  ", 32768, 1024, 4096, RFB_EPI_STORE, RFB_F32, bn);
+      bench("dec 8v q_proj  ", 32768, 1024, 1024, RFB_EPI_STORE, RFB_F32, bn);
+      bench("square 8192    ", 8192, 8192, 8192, RFB_EPI_STORE, RFB_BF16, bn);
+    }
+    bench("conv 256^2 128->128", 65536, 128, 1152, RFB_EPI_STORE, RFB_F16, 128, 256, 128);
+    bench("conv 512^2 128->64 ", 262144, 64, 1152, RFB_EPI_STORE, RFB_F16, 64, 512, 128);
+  }
+  return g_fail ? 1 : 0;
+}
