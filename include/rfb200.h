@@ -80,6 +80,39 @@ typedef struct {
 
 int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------
+ * rfb_attention: O = softmax(scale * Q K^T + mask) V, head_dim 128, bf16 in/out, fp32
+ * softmax and accumulation (tcgen05 flash-style kernel, S and O live in TMEM).
+ *
+ * Replaces F.scaled_dot_product_attention / flash_attn_* at layers/attention.py:143-198
+ * (encoder self-attention and decoder cross-attention, key-padding mask fused) and the
+ * per-window SDPA of SwinSelfAttention at layers/attention.py:349-358 (mode 1: the
+ * window partition and the shifted-window region mask become a group-id equality test).
+ *
+ * Layouts: Q [B][Nq][ldq], K [B][Nk][ldk] with head h in columns [h*128, h*128+128);
+ * Vt [B][H*128][ldvt] = V transposed (keys contiguous).  A batch stride of 0 on K / Vt /
+ * mask shares that tensor across the batch (hoisted per-scene K/V).
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+  int B, H, Nq, Nk;
+  const void* Q;
+  long long ldq, q_batch_stride;
+  const void* K;
+  long long ldk, k_batch_stride;
+  const void* Vt;
+  long long ldvt, vt_batch_stride;
+  void* O;
+  long long ldo, o_batch_stride;
+  const uint32_t* key_mask_bits; /* mode 0: [B][4*ceil(Nk/128)] packed bits, 1 = attend; NULL = all */
+  long long mask_batch_stride_words;
+  int mode;                /* 0 = dense over all keys, 1 = block-diagonal 128-token tiles */
+  const uint8_t* group_id; /* mode 1: [group_period]; i,j attend iff ids equal */
+  int group_period;
+  float scale;
+} rfb_attn_args;
+
+int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

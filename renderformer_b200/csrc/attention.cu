@@ -1,0 +1,388 @@
+// Flash-style attention on tcgen05 / TMEM for head_dim = 128 (sm_100a).
+//
+//   O = softmax(scale * Q K^T + mask) V        per (batch, head, 128-query tile)
+//
+// One CTA per query tile.  Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = softmax (one thread per query row).  S = Q K^T is double-buffered in TMEM
+// (2 x 128 fp32 columns), O accumulates in TMEM (128 columns); P is written as bf16 into a
+// 128B-swizzled smem tile and fed back as the A operand of P V.  V is consumed transposed
+// ([head_dim, keys], keys contiguous) so every operand is K-major.
+//
+// mode 0: every query tile visits all key tiles; keys are masked by a packed bit mask
+//         (the key-padding mask of layers/attention.py:145-161, True = attend).
+// mode 1: block-diagonal -- query tile i only sees key tile i and tokens attend iff their
+//         group ids are equal (two 64-token swin windows per tile, plus the shifted-window
+//         region id: layers/attention.py:238-271,327-358).
+#include <atomic>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace rfb {
+
+extern std::atomic<long long> g_launch_count;
+
+struct AttnKParams {
+  int Nq, Nk, H;
+  int n_kv_tiles;
+  int mode;
+  int k_batched, v_batched;  // 0: batch coordinate pinned to 0 (shared across the grid's batch dim)
+  const uint32_t* mask_bits;
+  long long mask_stride_words;
+  const uint8_t* group_id;
+  int group_period;
+  void* O;
+  long long ldo, o_batch_stride;
+  float scale_log2;
+};
+
+constexpr uint32_t kTileBytes = 128 * 128 * 2;  // one 128 x 128 bf16 operand tile (two SW128 halves)
+constexpr uint32_t kHalfBytes = 128 * 64 * 2;
+constexpr int kKVStages = 2;
+constexpr uint32_t kAttnSmem = kTileBytes * (1 + 2 * kKVStages + 1) + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+    attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kTileBytes;
+  uint8_t* sP = sV + kKVStages * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileBytes);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = q_full + 1;            // kKVStages
+  uint64_t* k_empty = k_full + kKVStages;   // kKVStages
+  uint64_t* v_full = k_empty + kKVStages;   // kKVStages
+  uint64_t* v_empty = v_full + kKVStages;   // kKVStages
+  uint64_t* s_full = v_empty + kKVStages;   // 2
+  uint64_t* s_empty = s_full + 2;           // 2
+  uint64_t* p_full = s_empty + 2;           // 1
+  uint64_t* pv_done = p_full + 1;           // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint8_t* s_gid = reinterpret_cast<uint8_t*>(tmem_slot + 2);  // 128 group ids (mode 1)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKVStages; ++i) {
+      mbar_init(&k_full[i], 1), mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1), mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ), tma_prefetch_desc(&tmK), tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (p.mode == 1 && threadIdx.x >= 64) {
+    const int i = threadIdx.x - 64;
+    s_gid[i] = p.group_id[(q0 + i) % p.group_period];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;         // + 128 * (j & 1)
+  const uint32_t tO = tmem_base + 256;
+
+  const int n_tiles = (p.mode == 1) ? 1 : p.n_kv_tiles;
+  const int kb = p.k_batched ? b : 0;
+  const int vb = p.v_batched ? b : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tmQ, q_full, h * 128, q0, b);
+      tma_load_3d(sQ + kHalfBytes, &tmQ, q_full, h * 128 + 64, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        const int key0 = ((p.mode == 1) ? qt : j) * 128;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        tma_load_3d(sK + s * kTileBytes, &tmK, &k_full[s], h * 128, key0, kb);
+        tma_load_3d(sK + s * kTileBytes + kHalfBytes, &tmK, &k_full[s], h * 128 + 64, key0, kb);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        tma_load_3d(sV + s * kTileBytes, &tmV, &v_full[s], key0, h * 128, vb);
+        tma_load_3d(sV + s * kTileBytes + kHalfBytes, &tmV, &v_full[s], key0 + 64, h * 128, vb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
+      auto issue_qk = [&](int j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        const int sb = j & 1;
+        mbar_wait(&k_full[s], ph);
+        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sQ));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sK + s * kTileBytes));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
+          umma_f16(tS + sb * 128, ad + off, bd + off, idesc, k != 0);
+        }
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[sb]);
+      };
+      auto issue_pv = [&](int j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sP));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sV + s * kTileBytes));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
+          umma_f16(tO, ad + off, bd + off, idesc, (j | k) != 0);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        issue_pv(j);
+      }
+    }
+  } else {
+    // ------------------------------ softmax warps ------------------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (p.mode == 1) {
+      const uint8_t g = s_gid[r];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t bits = 0;
+        for (int i = 0; i < 32; ++i) bits |= (s_gid[w * 32 + i] == g ? 1u : 0u) << i;
+        // keys past the end of the sequence never attend
+        mw[w] = bits;
+      }
+      const int rem = p.Nk - q0;
+      if (rem < 128) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int lo = w * 32;
+          const uint32_t keep = rem <= lo ? 0u : (rem - lo >= 32 ? 0xffffffffu : ((1u << (rem - lo)) - 1u));
+          mw[w] &= keep;
+        }
+      }
+    }
+    uint8_t* prow = sP + r * 128;
+    const uint32_t rx = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1;
+      if (p.mode == 0) {
+        if (p.mask_bits) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+              p.mask_bits + static_cast<long long>(b) * p.mask_stride_words + j * 4));
+          mw[0] = u.x, mw[1] = u.y, mw[2] = u.z, mw[3] = u.w;
+        } else {
+          const int rem = p.Nk - j * 128;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int lo = w * 32;
+            mw[w] = rem <= lo ? 0u : (rem - lo >= 32 ? 0xffffffffu : ((1u << (rem - lo)) - 1u));
+          }
+        }
+      }
+      const bool all_valid = (mw[0] & mw[1] & mw[2] & mw[3]) == 0xffffffffu;
+
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tS + sb * 128 + lane_addr;
+
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_wait_ld();
+        if (all_valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+          const uint32_t bits = mw[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((bits >> i) & 1u) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_f((m_run - m_use) * sl2);
+      const float neg_ms = -m_use * sl2;
+
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O stable, P tile free
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_addr + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + lane_addr + c * 32, v);
+          }
+          tmem_wait_st();
+        }
+      }
+
+      // pass 2: P = exp2(s*sl2 - m*sl2) -> bf16 -> swizzled smem
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_wait_ld();
+        float pv[32];
+        if (all_valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = ex2_f(fmaf(__uint_as_float(v[i]), sl2, neg_ms));
+        } else {
+          const uint32_t bits = mw[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            pv[i] = ((bits >> i) & 1u) ? ex2_f(fmaf(__uint_as_float(v[i]), sl2, neg_ms)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+        uint8_t* dst = prow + (c >> 1) * kHalfBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(pv[i * 8 + 0], pv[i * 8 + 1]);
+          u.y = pack_bf16(pv[i * 8 + 2], pv[i * 8 + 3]);
+          u.z = pack_bf16(pv[i * 8 + 4], pv[i * 8 + 5]);
+          u.w = pack_bf16(pv[i * 8 + 6], pv[i * 8 + 7]);
+          const uint32_t chunk = ((c & 1) * 4 + i) ^ rx;
+          *reinterpret_cast<uint4*>(dst + chunk * 16) = u;
+        }
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(p_full);
+      }
+    }
+
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+    const bool row_ok = (q0 + r) < p.Nq;
+    uint16_t* orow = static_cast<uint16_t*>(p.O) + static_cast<long long>(b) * p.o_batch_stride +
+                     static_cast<long long>(q0 + r) * p.ldo + h * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + c * 32, v);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace rfb
+
+using namespace rfb;
+
+extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a || !a->Q || !a->K || !a->Vt || !a->O || a->B <= 0 || a->H <= 0 || a->Nq <= 0 || a->Nk <= 0)
+    return RFB_ERR_ARG;
+  if (a->mode == 1 && (!a->group_id || a->group_period <= 0 || a->Nq != a->Nk)) return RFB_ERR_ARG;
+  if (a->ldo % 8) return RFB_ERR_ALIGN;
+
+  const uint64_t hd_cols = (uint64_t)a->H * 128;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    uint64_t dims[3] = {hd_cols, (uint64_t)a->Nq, (uint64_t)a->B};
+    uint64_t st[2] = {(uint64_t)a->ldq * 2, (uint64_t)(a->B > 1 ? a->q_batch_stride : (long long)a->Nq * a->ldq) * 2};
+    if ((rc = make_tmap_16b(&tmQ, RFB_BF16, a->Q, 3, dims, st, box)) != RFB_OK) return rc;
+  }
+  const int k_batched = (a->B > 1 && a->k_batch_stride != 0);
+  const int v_batched = (a->B > 1 && a->vt_batch_stride != 0);
+  {
+    uint64_t dims[3] = {hd_cols, (uint64_t)a->Nk, (uint64_t)(k_batched ? a->B : 1)};
+    uint64_t st[2] = {(uint64_t)a->ldk * 2, (uint64_t)(k_batched ? a->k_batch_stride : (long long)a->Nk * a->ldk) * 2};
+    if ((rc = make_tmap_16b(&tmK, RFB_BF16, a->K, 3, dims, st, box)) != RFB_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->Nk, hd_cols, (uint64_t)(v_batched ? a->B : 1)};
+    uint64_t st[2] = {(uint64_t)a->ldvt * 2, (uint64_t)(v_batched ? a->vt_batch_stride : (long long)hd_cols * a->ldvt) * 2};
+    if ((rc = make_tmap_16b(&tmV, RFB_BF16, a->Vt, 3, dims, st, box)) != RFB_OK) return rc;
+  }
+
+  AttnKParams p{};
+  p.Nq = a->Nq, p.Nk = a->Nk, p.H = a->H;
+  p.n_kv_tiles = (a->Nk + 127) / 128;
+  p.mode = a->mode;
+  p.k_batched = k_batched, p.v_batched = v_batched;
+  p.mask_bits = a->key_mask_bits;
+  p.mask_stride_words = a->mask_batch_stride_words;
+  p.group_id = a->group_id, p.group_period = a->group_period;
+  p.O = a->O, p.ldo = a->ldo, p.o_batch_stride = a->o_batch_stride;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
+        cudaSuccess)
+      return RFB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  dim3 grid((a->Nq + 127) / 128, a->H, a->B);
+  attn_tc_kernel<<<grid, 192, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+  g_launch_count++;
+  return check_launch("attn_tc_kernel");
+}
