@@ -106,12 +106,68 @@ typedef struct {
   const uint32_t* key_mask_bits; /* mode 0: [B][4*ceil(Nk/128)] packed bits, 1 = attend; NULL = all */
   long long mask_batch_stride_words;
   int mode;                /* 0 = dense over all keys, 1 = block-diagonal 128-token tiles */
-  const uint8_t* group_id; /* mode 1: [group_period]; i,j attend iff ids equal */
+  const uint8_t* group_id; /* mode 1: [group_period] region ids; i,j attend iff same 64-token
+                              half of the tile and equal ids */
   int group_period;
   float scale;
 } rfb_attn_args;
 
 int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * Row kernels (one warp per row, fp32 math, 128-bit accesses).
+ * ------------------------------------------------------------------------------- */
+
+/* out[r,:] = RMSNorm(x[gather ? gather[r] : r, :]) * w -- nn.RMSNorm at layers/attention.py:
+ * 436-482 as used in AttentionLayer.forward :503,508,516,526.  `gather` folds torch.roll +
+ * window_partition (:334-339) into the read.  out_dtype RFB_F32/BF16/F16. */
+int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* out, int out_dtype, long long ldo,
+                int rows, int d, float eps, const int* gather, rfb_stream_t stream);
+
+/* QK-RMSNorm over the full model width + triangle RoPE (layers/attention.py:128-141,
+ * encodings/rope.py:78-149,152-206): fp32 [rows, nseg*d] -> bf16.  Input row = r % in_period
+ * when in_period > 0 (one hoisted pre-RoPE K re-rotated for every view).  pos [rows,9] or NULL. */
+int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out, long long ldo,
+                    int rows, int d, int nseg, float eps, const float* pos, const float* freqs, int nfreq,
+                    rfb_stream_t stream);
+
+/* out[b, n_prefix + i, :] = token + RMSNorm(a[b,i]) * wa (+ RMSNorm(b[b,i]) * wb); rows
+ * [0,n_prefix) = prefix; rows past n_prefix + rows_in are zero.  models/renderformer.py:139-163,
+ * models/view_transformer.py:108.  eps = fp32 machine epsilon (nn.RMSNorm(eps=None)). */
+int rfb_token_assemble(const float* a, const float* wa, const float* b, const float* wb, const float* token,
+                       const float* prefix, int n_prefix, float* out, int rows_in, int rows_out, int batch,
+                       int d, rfb_stream_t stream);
+
+/* texture fp32 [n_tris, channels, texels] -> f16, log10(x+1) on the last log_channels channels
+ * (pipelines/rendering_pipeline.py:67-68; does not touch the caller's tensor). */
+int rfb_texture_prep(const float* tex, void* out, long long n_tris, int channels, int texels,
+                     int log_channels, rfb_stream_t stream);
+
+/* NeRF encoding of vertex normals [n,9] -> f16 [n, ld] (encodings/nerf_encoding.py:63-84). */
+int rfb_vn_encode(const float* vn, void* out, int n, int nfreq, int ld, rfb_stream_t stream);
+
+/* camera-space ray bundles -> patch tokens f16 [V, (R/8)^2, 192] (utils/ray_generator.py:13-50,
+ * models/view_transformer.py:104-107); fov in degrees. */
+int rfb_ray_tokens(const float* fov_deg, void* out, int n_views, int resolution, rfb_stream_t stream);
+
+/* RoPE positions [V, rows_out, 9]: register rows = masked centroid, then T_v^-1 * triangle
+ * (models/renderformer.py:103-124, utils/transform.py:7-27).  c2w NULL = world space. */
+int rfb_positions(const float* tri, const uint8_t* mask, const float* c2w, float* pos, int n, int n_reg,
+                  int rows_out, int n_views, rfb_stream_t stream);
+
+/* bool key mask [batch, n] -> packed bits [batch, words] behind n_prefix always-valid keys. */
+int rfb_pack_mask(const uint8_t* mask, uint32_t* bits, int n, int n_prefix, int words, int batch,
+                  rfb_stream_t stream);
+
+int rfb_cast(const float* x, void* out, int out_dtype, long long n, rfb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * DPT decoder helpers, NHWC f16 (layers/dpt.py:154-155,195-213).
+ * ------------------------------------------------------------------------------- */
+int rfb_pixel_shuffle(const void* in, void* out, int B, int h, int w, int s, int C, rfb_stream_t stream);
+int rfb_im2col_s2(const void* in, void* out, int B, int H, int W, int C, rfb_stream_t stream);
+int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                          rfb_stream_t stream);
 
 #ifdef __cplusplus
 }

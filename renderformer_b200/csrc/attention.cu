@@ -10,9 +10,9 @@
 //
 // mode 0: every query tile visits all key tiles; keys are masked by a packed bit mask
 //         (the key-padding mask of layers/attention.py:145-161, True = attend).
-// mode 1: block-diagonal -- query tile i only sees key tile i and tokens attend iff their
-//         group ids are equal (two 64-token swin windows per tile, plus the shifted-window
-//         region id: layers/attention.py:238-271,327-358).
+// mode 1: block-diagonal -- query tile i only sees key tile i; a tile holds two 64-token swin
+//         windows and tokens attend iff they sit in the same window (tile half) and carry the
+//         same shifted-window region id (layers/attention.py:238-271,327-358).
 #include <atomic>
 
 #include "host_util.h"
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         uint32_t bits = 0;
-        for (int i = 0; i < 32; ++i) bits |= (s_gid[w * 32 + i] == g ? 1u : 0u) << i;
-        // keys past the end of the sequence never attend
+        for (int i = 0; i < 32; ++i)  // same 64-token window (tile half) and same region id
+          bits |= ((s_gid[w * 32 + i] == g && ((w * 32 + i) >> 6) == (r >> 6)) ? 1u : 0u) << i;
         mw[w] = bits;
       }
       const int rem = p.Nk - q0;

@@ -1,0 +1,142 @@
+// Bandwidth-bound helpers of the DPT patch decoder (layers/dpt.py), NHWC fp16 activations:
+// ConvTranspose(k = s) pixel-shuffle scatter, im2col for the stride-2 3x3 conv, and bilinear
+// align_corners=True resampling.  All convolutions themselves run through rfb_gemm.
+#include <atomic>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace rfb {
+
+extern std::atomic<long long> g_launch_count;
+
+// in [B*h*w, s*s*C] with column = (i*s + j)*C + c  ->  out NHWC [B, h*s, w*s, C]
+//   (ConvTranspose2d kernel == stride: layers/dpt.py:195-206; the GEMM adds the bias)
+__global__ void pixel_shuffle_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h,
+                                     int w, int s, int C8) {
+  const long long total = (long long)B * h * w * s * s * C8;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    long long r = t / C8;
+    const int j = r % s;
+    r /= s;
+    const int i = r % s;
+    r /= s;
+    const int x = r % w;
+    r /= w;
+    const int y = r % h;
+    const int b = r / h;
+    const long long o = (((long long)b * h * s + (y * s + i)) * (w * s) + (x * s + j)) * C8 + c;
+    out[o] = __ldg(in + t);
+  }
+}
+
+// in NHWC [B,H,W,C] -> out [B*Ho*Wo, 9*C] (tap-major, channel-minor), kernel 3, stride 2, pad 1
+//   (resize_layers[3]: layers/dpt.py:208-213)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                                 int C8, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo * 9 * C8;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    long long r = t / C8;
+    const int tap = r % 9;
+    r /= 9;
+    const int xo = r % Wo;
+    r /= Wo;
+    const int yo = r % Ho;
+    const int b = r / Ho;
+    const int y = yo * 2 - 1 + tap / 3, x = xo * 2 - 1 + tap % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(in + (((long long)b * H + y) * W + x) * C8 + c);
+    out[t] = v;
+  }
+}
+
+__device__ __forceinline__ void h8_to_f(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
+
+// bilinear, align_corners=True: src = dst * (in-1)/(out-1)   (F.interpolate, layers/dpt.py:154-155)
+__global__ void upsample_bilinear_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int Hi,
+                                         int Wi, int Ho, int Wo, int C8) {
+  const long long total = (long long)B * Ho * Wo * C8;
+  const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    long long r = t / C8;
+    const int xo = r % Wo;
+    r /= Wo;
+    const int yo = r % Ho;
+    const int b = r / Ho;
+    const float fy = yo * sy, fx = xo * sx;
+    int y0 = (int)fy, x0 = (int)fx;
+    y0 = min(y0, Hi - 1), x0 = min(x0, Wi - 1);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const uint4* base = in + (long long)b * Hi * Wi * C8 + c;
+    float a[8], bb[8], cc[8], d[8];
+    h8_to_f(__ldg(base + ((long long)y0 * Wi + x0) * C8), a);
+    h8_to_f(__ldg(base + ((long long)y0 * Wi + x1) * C8), bb);
+    h8_to_f(__ldg(base + ((long long)y1 * Wi + x0) * C8), cc);
+    h8_to_f(__ldg(base + ((long long)y1 * Wi + x1) * C8), d);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float top = a[i] + (bb[i] - a[i]) * wx;
+      const float bot = cc[i] + (d[i] - cc[i]) * wx;
+      o[i] = top + (bot - top) * wy;
+    }
+    uint4 u;
+    u.x = pack_f16(o[0], o[1]), u.y = pack_f16(o[2], o[3]), u.z = pack_f16(o[4], o[5]), u.w = pack_f16(o[6], o[7]);
+    out[t] = u;
+  }
+}
+
+static inline int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = 148LL * 32;
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace rfb
+
+using namespace rfb;
+
+extern "C" int rfb_pixel_shuffle(const void* in, void* out, int B, int h, int w, int s, int C,
+                                 rfb_stream_t stream) {
+  if (!in || !out || C % 8 || s < 1) return RFB_ERR_ARG;
+  const long long total = (long long)B * h * w * s * s * (C / 8);
+  pixel_shuffle_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, h, w,
+                                                                          s, C / 8);
+  g_launch_count++;
+  return check_launch("pixel_shuffle_kernel");
+}
+
+extern "C" int rfb_im2col_s2(const void* in, void* out, int B, int H, int W, int C, rfb_stream_t stream) {
+  if (!in || !out || C % 8) return RFB_ERR_ARG;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W,
+                                                                      C / 8, Ho, Wo);
+  g_launch_count++;
+  return check_launch("im2col_s2_kernel");
+}
+
+extern "C" int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                     rfb_stream_t stream) {
+  if (!in || !out || C % 8) return RFB_ERR_ARG;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  upsample_bilinear_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B,
+                                                                              Hi, Wi, Ho, Wo, C / 8);
+  g_launch_count++;
+  return check_launch("upsample_bilinear_kernel");
+}

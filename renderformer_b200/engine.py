@@ -1,0 +1,380 @@
+"""Host-side schedule of the RenderFormer forward pass on the sm_100a kernels.
+
+Two stages, mirroring the reference's structure (models/renderformer.py:171-206):
+
+* `encode_scene`  -- view-independent: token construction + triangle-token encoder, run once
+  per scene; additionally hoists the decoder's per-layer K / V projections of the triangle
+  tokens, which do not depend on the view.
+* `render_views`  -- view-dependent: ray-bundle tokens, decoder (cross-attention to the hoisted
+  K/V with per-view K RoPE, swin or full self-attention, SwiGLU), DPT head, HDR decode.
+
+All math runs in the C-ABI kernels (ops.py); torch provides buffers and streams only.
+Precision policy: fp32 residual stream, bf16 tensor-core operands in the transformer stacks,
+fp16 operands in the token encoders and the DPT head, fp32 accumulation / softmax / norms.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+from . import ops
+from .config import RenderFormerConfig
+
+EPS = 1e-6  # reference: layers/attention.py:16
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class SceneState:
+    """Per-scene device state handed from the view-independent to the view-dependent stage."""
+    B: int
+    N: int
+    Nt: int
+    Ntp: int
+    seq: torch.Tensor        # fp32 [B, Ntp, d]
+    tri: torch.Tensor        # fp32 [B, N, 9]
+    mask_u8: torch.Tensor    # uint8 [B, N]
+    mask_bits: torch.Tensor  # int32 [B, words]
+    k_pre: List[torch.Tensor]  # per decoder layer fp32 [B, Ntp, dv]  (pre-norm, pre-RoPE)
+    v_t: List[torch.Tensor]    # per decoder layer bf16 [B, dv, Ntp]  (transposed)
+
+    def tensors(self):
+        return [self.seq, self.tri, self.mask_u8, self.mask_bits] + self.k_pre + self.v_t
+
+
+def swin_window_maps(Hp: int, Wp: int, shift: int, ws: int = 8):
+    """Window-order -> token-order permutation and shifted-window region ids.
+
+    Row w of the window-major layout holds token perm[w] of the row-major (Hp x Wp) grid, i.e.
+    torch.roll(-shift) followed by window_partition (layers/attention.py:205-218,334-339); region
+    ids are the closed form of get_swin_attn_mask (:238-271)."""
+    w = torch.arange(Hp * Wp)
+    win, p = w // (ws * ws), w % (ws * ws)
+    ry = (win // (Wp // ws)) * ws + p // ws
+    rx = (win % (Wp // ws)) * ws + p % ws
+    perm = ((ry + shift) % Hp) * Wp + (rx + shift) % Wp
+    if shift > 0:
+        def rid(r, n):
+            return (r >= n - ws).long() + (r >= n - shift).long()
+        region = 3 * rid(ry, Hp) + rid(rx, Wp)
+    else:
+        region = torch.zeros_like(w)
+    return perm.to(torch.int32), region.to(torch.uint8)
+
+
+class Engine:
+    def __init__(self, cfg: RenderFormerConfig, state_dict: Dict[str, torch.Tensor], device):
+        cfg.check_supported()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.RfbError("renderformer_b200.Engine needs a CUDA device (there is no CPU fallback)")
+        L.load()
+        self.w: Dict[str, torch.Tensor] = {}
+        self._maps: Dict[tuple, tuple] = {}
+        self._prepare(state_dict)
+
+    # ------------------------------------------------------------------ weights
+    def _prepare(self, sd: Dict[str, torch.Tensor]) -> None:
+        cfg, dev = self.cfg, self.device
+        bf, hf = torch.bfloat16, torch.float16
+
+        def g(k):
+            return sd[k].detach().to(dev, torch.float32)
+
+        def put(name, t, dt=None):
+            self.w[name] = (t if dt is None else t.to(dt)).contiguous()
+
+        def swiglu_w(p):
+            w1, w3 = g(p + "w1.weight"), g(p + "w3.weight")
+            f, d = w1.shape
+            return torch.stack([w1.view(f // 16, 16, d), w3.view(f // 16, 16, d)], dim=1).reshape(2 * f, d)
+
+        def conv_w(k):  # [Co, Ci, 3, 3] -> [Co, (ky*3+kx)*Ci + ci]
+            w = g(k)
+            return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+        d = cfg.latent_dim
+        put("tri_token", g("tri_token").reshape(-1))
+        put("reg_tokens", g("reg_tokens").reshape(cfg.num_register_tokens, d))
+        vw = g("vn_encoding_proj.weight")
+        self.vn_ld = _rup(vw.shape[1], 64)
+        vwp = torch.zeros((d, self.vn_ld), device=dev)
+        vwp[:, : vw.shape[1]] = vw
+        put("vn.w", vwp, hf), put("vn.b", g("vn_encoding_proj.bias")), put("vn.norm", g("vn_encoder_norm.weight"))
+        put("tex.w", g("texture_encoder.weight"), hf), put("tex.b", g("texture_encoder.bias"))
+        put("tex.norm", g("texture_encoder_norm.weight"))
+        put("enc.freqs", g("transformer.rope_emb.freqs"))
+        for i in range(cfg.num_layers):
+            p, o = f"transformer.layers.{i}.", f"enc{i}."
+            w_in = g(p + "multihead_attn.in_proj.weight")
+            put(o + "wqk", w_in[: 2 * d], bf), put(o + "wv", w_in[2 * d:], bf)
+            put(o + "wo", g(p + "multihead_attn.out_proj.weight"), bf)
+            put(o + "qkn", torch.cat([g(p + "multihead_attn.q_norm.weight"), g(p + "multihead_attn.k_norm.weight")]))
+            put(o + "n1", g(p + "query_norm.weight")), put(o + "n2", g(p + "ffn_norm.weight"))
+            put(o + "w13", swiglu_w(p + "ffn."), bf), put(o + "w2", g(p + "ffn.w2.weight"), bf)
+
+        v = "view_transformer."
+        dv = cfg.view_transformer_latent_dim
+        put("ray.token", g(v + "ray_map_patch_token").reshape(-1))
+        put("ray.w", g(v + "ray_map_encoder.weight"), hf), put("ray.b", g(v + "ray_map_encoder.bias"))
+        put("ray.norm", g(v + "ray_map_encoder_norm.weight"))
+        put("dec.freqs", g(v + "transformer.rope_emb.freqs"))
+        for i in range(cfg.view_transformer_n_layers):
+            p, o = v + f"transformer.layers.{i}.", f"dec{i}."
+            for nm in ("q", "k", "v", "out"):
+                put(o + "w" + nm, g(p + f"multihead_attn.{nm}_proj.weight"), bf)
+            put(o + "qn", g(p + "multihead_attn.q_norm.weight")), put(o + "kn", g(p + "multihead_attn.k_norm.weight"))
+            put(o + "n_q", g(p + "query_norm.weight")), put(o + "n_kv", g(p + "kv_norm.weight"))
+            w_in = g(p + "self_attn.in_proj.weight")
+            put(o + "s.wqk", w_in[: 2 * dv], bf), put(o + "s.wv", w_in[2 * dv:], bf)
+            put(o + "s.wo", g(p + "self_attn.out_proj.weight"), bf)
+            put(o + "s.qkn", torch.cat([g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight")]))
+            put(o + "n_s", g(p + "self_attn_norm.weight")), put(o + "n_f", g(p + "ffn_norm.weight"))
+            put(o + "w13", swiglu_w(p + "ffn."), bf), put(o + "w2", g(p + "ffn.w2.weight"), bf)
+
+        h = v + "out_dpt."
+        for i in range(4):
+            put(f"dpt.proj{i}.w", g(h + f"projects.{i}.weight").flatten(1), hf)
+            put(f"dpt.proj{i}.b", g(h + f"projects.{i}.bias"))
+            put(f"dpt.rn{i}.w", conv_w(h + f"scratch.layer{i + 1}_rn.weight"), hf)
+        for i, s in ((0, 4), (1, 2)):  # ConvTranspose2d(k = s): [Ci, Co, s, s] -> [(i*s+j)*Co + co, ci]
+            w = g(h + f"resize_layers.{i}.weight")
+            put(f"dpt.up{i}.w", w.permute(2, 3, 1, 0).reshape(s * s * w.shape[1], w.shape[0]), hf)
+            put(f"dpt.up{i}.b", g(h + f"resize_layers.{i}.bias").repeat(s * s))
+        put("dpt.down3.w", conv_w(h + "resize_layers.3.weight"), hf), put("dpt.down3.b", g(h + "resize_layers.3.bias"))
+        for r in (1, 2, 3, 4):
+            p = h + f"scratch.refinenet{r}."
+            put(f"dpt.rf{r}.out.w", g(p + "out_conv.weight").flatten(1), hf), put(f"dpt.rf{r}.out.b", g(p + "out_conv.bias"))
+            for u in ((1, 2) if r != 4 else (2,)):
+                for c in (1, 2):
+                    put(f"dpt.rf{r}.u{u}c{c}.w", conv_w(p + f"resConvUnit{u}.conv{c}.weight"), hf)
+                    put(f"dpt.rf{r}.u{u}c{c}.b", g(p + f"resConvUnit{u}.conv{c}.bias"))
+        put("dpt.oc1.w", conv_w(h + "scratch.output_conv1.weight"), hf), put("dpt.oc1.b", g(h + "scratch.output_conv1.bias"))
+        put("dpt.oc2.w", conv_w(h + "scratch.output_conv2.0.weight"), hf), put("dpt.oc2.b", g(h + "scratch.output_conv2.0.bias"))
+        put("dpt.oc3.w", g(h + "scratch.output_conv2.2.weight").flatten(1)), put("dpt.oc3.b", g(h + "scratch.output_conv2.2.bias"))
+
+    def _e(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ shared blocks
+    def _ffn(self, x, rows, d, n_w, w13, w2):
+        """x += w2(silu(w1 n(x)) * w3 n(x))   layers/attention.py:56-57,526."""
+        h = ops.rmsnorm(x, n_w, self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
+        g = ops.gemm(h, w13, epi=L.EPI_SWIGLU, out_dtype=torch.bfloat16)
+        ops.gemm(g, w2, out=x, res1=x)
+
+    # ------------------------------------------------------------------ stage 1
+    @torch.no_grad()
+    def encode_scene(self, triangles, texture, mask, vn, texture_is_log: bool = False) -> SceneState:
+        cfg, w, dev = self.cfg, self.w, self.device
+        B, N = triangles.shape[:2]
+        d, H = cfg.latent_dim, cfg.num_heads
+        nreg = cfg.num_register_tokens
+        Nt, Ntp = N + nreg, _rup(N + nreg, 8)
+        tri = triangles.reshape(B, N, 9).to(dev, torch.float32).contiguous()
+        vn9 = vn.reshape(B, N, 9).to(dev, torch.float32).contiguous()
+        tex = texture.to(dev, torch.float32).contiguous()
+        mask_u8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8)
+        C_, P = cfg.texture_channels, cfg.texture_encode_patch_size
+
+        # token construction  (models/renderformer.py:126-169)
+        tex16 = ops.texture_prep(tex, self._e((B * N, C_ * P * P), torch.float16), n_tris=B * N, channels=C_,
+                                 texels=P * P, log_channels=0 if (cfg.use_ldr or texture_is_log) else 3)
+        tex_lin = ops.gemm(tex16, w["tex.w"], bias=w["tex.b"], out_dtype=torch.float32)
+        del tex16
+        vn16 = ops.vn_encode(vn9, self._e((B * N, self.vn_ld), torch.float16), n=B * N, nfreq=cfg.vn_pe_num_freqs,
+                             ld=self.vn_ld)
+        vn_lin = ops.gemm(vn16, w["vn.w"], bias=w["vn.b"], out_dtype=torch.float32)
+        x = self._e((B * Ntp, d), torch.float32)
+        ops.token_assemble(tex_lin, w["tex.norm"], vn_lin, w["vn.norm"], w["tri_token"], w["reg_tokens"], x,
+                           n_prefix=nreg, rows_in=N, rows_out=Ntp, batch=B, d=d)
+        pos = self._e((B, Ntp, 9), torch.float32)
+        for b in range(B):
+            ops.positions(tri[b], mask_u8[b], None, pos[b], n=N, n_reg=nreg, rows_out=Ntp, n_views=1)
+        words = 4 * ((Ntp + 127) // 128)
+        bits = ops.pack_mask(mask_u8, self._e((B, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=B)
+
+        # encoder  (layers/attention.py:579-590)
+        rows = B * Ntp
+        for i in range(cfg.num_layers):
+            o = f"enc{i}."
+            h = ops.rmsnorm(x, w[o + "n1"], self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
+            qk = ops.gemm(h, w[o + "wqk"], out_dtype=torch.float32)
+            vt = self._e((B, d, Ntp), torch.bfloat16)
+            for b in range(B):
+                ops.gemm(w[o + "wv"], h[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp)
+            qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((rows, 2 * d), torch.bfloat16), rows=rows, d=d, nseg=2,
+                                  ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
+            att = self._e((rows, d), torch.bfloat16)
+            ops.attention(qkr, qkr[:, d:], vt, att, B=B, H=H, Nq=Ntp, Nk=Ntp, ldq=2 * d, ldk=2 * d, ldvt=Ntp, ldo=d,
+                          q_bs=Ntp * 2 * d, k_bs=Ntp * 2 * d, vt_bs=d * Ntp, o_bs=Ntp * d, mask_bits=bits,
+                          mask_bs=words)
+            ops.gemm(att, w[o + "wo"], out=x, res1=x)
+            self._ffn(x, rows, d, w[o + "n2"], w[o + "w13"], w[o + "w2"])
+
+        # hoisted decoder K / V projections of the triangle tokens (view independent)
+        dv = cfg.view_transformer_latent_dim
+        k_pre, v_t = [], []
+        for i in range(cfg.view_transformer_n_layers):
+            o = f"dec{i}."
+            c = ops.rmsnorm(x, w[o + "n_kv"], self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
+            k_pre.append(ops.gemm(c, w[o + "wk"], out_dtype=torch.float32).view(B, Ntp, dv))
+            vt = self._e((B, dv, Ntp), torch.bfloat16)
+            for b in range(B):
+                ops.gemm(w[o + "wv"], c[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp)
+            v_t.append(vt)
+        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
+
+    # ------------------------------------------------------------------ stage 2
+    def _swin_maps(self, Hp, Wp, shift, V):
+        key = (Hp, Wp, shift, V)
+        if key not in self._maps:
+            perm, region = swin_window_maps(Hp, Wp, shift)
+            n = Hp * Wp
+            full = (perm[None, :] + (torch.arange(V, dtype=torch.int32) * n)[:, None]).reshape(-1)
+            self._maps[key] = (full.to(self.device).contiguous(), region.to(self.device).contiguous())
+        return self._maps[key]
+
+    @torch.no_grad()
+    def render_views(self, st: SceneState, b: int, c2w: torch.Tensor, fov_deg: torch.Tensor, resolution: int,
+                     taps: Optional[dict] = None) -> torch.Tensor:
+        """Render V views of scene `b`.  c2w [V,4,4], fov_deg [V] or [V,1] -> HDR fp32 [V,R,R,3]."""
+        cfg, w, dev = self.cfg, self.w, self.device
+        V, R = c2w.shape[0], resolution
+        if R % 64 != 0 and cfg.view_transformer_use_swin_attn:
+            raise ValueError("resolution must be a multiple of 64 for swin attention")
+        if R % 8 != 0:
+            raise ValueError("resolution must be a multiple of the 8-pixel patch size")
+        Hp = Wp = R // 8
+        Nr = Hp * Wp
+        dv, Hh = cfg.view_transformer_latent_dim, cfg.view_transformer_n_heads
+        Ntp, N = st.Ntp, st.N
+        rows = V * Nr
+        bf = torch.bfloat16
+        c2w = c2w.to(dev, torch.float32).contiguous()
+        fov = fov_deg.reshape(-1).to(dev, torch.float32).contiguous()
+
+        pos = ops.positions(st.tri[b], st.mask_u8[b], c2w, self._e((V, Ntp, 9), torch.float32), n=N,
+                            n_reg=cfg.num_register_tokens, rows_out=Ntp, n_views=V)
+        rt = ops.ray_tokens(fov, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
+        lin = ops.gemm(rt, w["ray.w"], bias=w["ray.b"], out_dtype=torch.float32)
+        x = self._e((rows, dv), torch.float32)
+        ops.token_assemble(lin, w["ray.norm"], None, None, w["ray.token"], None, x, n_prefix=0, rows_in=rows,
+                           rows_out=rows, batch=1, d=dv)
+        words = st.mask_bits.shape[1]
+        feats = []
+        for i in range(cfg.view_transformer_n_layers):
+            o = f"dec{i}."
+            # cross-attention to the triangle tokens  (layers/attention.py:503-513)
+            h = ops.rmsnorm(x, w[o + "n_q"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS)
+            qf = ops.gemm(h, w[o + "wq"], out_dtype=torch.float32)
+            q = ops.qknorm_rope(qf, w[o + "qn"], self._e((rows, dv), bf), rows=rows, d=dv, nseg=1, ldx=dv, ldo=dv,
+                                eps=EPS)  # camera-space ray origin is 0: query RoPE is the identity (E5)
+            k = ops.qknorm_rope(st.k_pre[i][b], w[o + "kn"], self._e((V * Ntp, dv), bf), rows=V * Ntp, d=dv, nseg=1,
+                                ldx=dv, ldo=dv, in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
+            att = self._e((rows, dv), bf)
+            ops.attention(q, k, st.v_t[i][b], att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
+                          q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0)
+            ops.gemm(att, w[o + "wout"], out=x, res1=x)
+
+            # self-attention among ray tokens  (layers/attention.py:515-523)
+            if cfg.view_transformer_use_swin_attn:
+                perm, region = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
+                hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS, gather=perm)
+                qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
+                vt = ops.gemm(w[o + "s.wv"], hs, out=self._e((dv, rows), bf), N=rows)
+                qkn = ops.qknorm_rope(qk, w[o + "s.qkn"], self._e((rows, 2 * dv), bf), rows=rows, d=dv, nseg=2,
+                                      ldx=2 * dv, ldo=2 * dv, eps=EPS)
+                ops.attention(qkn, qkn[:, dv:], vt, att, B=1, H=Hh, Nq=rows, Nk=rows, ldq=2 * dv, ldk=2 * dv,
+                              ldvt=rows, ldo=dv, mode=1, group_id=region, group_period=Nr)
+                ops.gemm(att, w[o + "s.wo"], out=x, res1=x, row_map=perm)
+            else:
+                hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS)
+                qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
+                Nrp = _rup(Nr, 8)
+                vt = self._e((V, dv, Nrp), bf)
+                for vi in range(V):
+                    ops.gemm(w[o + "s.wv"], hs[vi * Nr:(vi + 1) * Nr], out=vt[vi], N=Nr)
+                qkn = ops.qknorm_rope(qk, w[o + "s.qkn"], self._e((rows, 2 * dv), bf), rows=rows, d=dv, nseg=2,
+                                      ldx=2 * dv, ldo=2 * dv, eps=EPS)  # ray RoPE is the identity
+                ops.attention(qkn, qkn[:, dv:], vt, att, B=V, H=Hh, Nq=Nr, Nk=Nr, ldq=2 * dv, ldk=2 * dv, ldvt=Nrp,
+                              ldo=dv, q_bs=Nr * 2 * dv, k_bs=Nr * 2 * dv, vt_bs=dv * Nrp, o_bs=Nr * dv)
+                ops.gemm(att, w[o + "s.wo"], out=x, res1=x)
+            self._ffn(x, rows, dv, w[o + "n_f"], w[o + "w13"], w[o + "w2"])
+            if i in cfg.out_layers:
+                feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
+                if taps is not None:
+                    taps.setdefault("dec_feats", []).append(x.clone().view(V, Nr, dv))
+        return self._dpt(feats, V, Hp, Wp)
+
+    # ------------------------------------------------------------------ DPT head (layers/dpt.py:242-273)
+    def _conv(self, x, name, B, H, W, Cin, **kw):
+        return ops.gemm(x, self.w[name + ".w"], conv=(B, H, W, Cin), **kw)
+
+    def _rcu(self, x_raw, x_act, name, B, H, W, extra_res=None, want_act=False):
+        """x + conv2(silu(conv1(silu(x))))  (+ extra_res)   layers/dpt.py:76-92,139-143."""
+        F_ = self.cfg.dpt_features
+        hf = torch.float16
+        t = self._e((B * H * W, F_), hf)
+        self._conv(x_act, name + "c1", B, H, W, F_, bias=self.w[name + "c1.b"], out=None, out_act=t)
+        out = self._e((B * H * W, F_), hf)
+        act = self._e((B * H * W, F_), hf) if want_act else None
+        self._conv(t, name + "c2", B, H, W, F_, bias=self.w[name + "c2.b"], res1=x_raw, res2=extra_res, out=out,
+                   out_act=act)
+        return out, act
+
+    def _fusion(self, r, B, H, W, Ho, Wo, x0, x1_raw=None, x1_act=None, x0_act=None):
+        """FeatureFusionBlock (layers/dpt.py:133-159); the 1x1 out_conv runs before the bilinear
+        resize, with which it commutes."""
+        F_ = self.cfg.dpt_features
+        hf = torch.float16
+        name = f"dpt.rf{r}."
+        if x1_raw is not None:
+            s_raw, s_act = self._rcu(x1_raw, x1_act, name + "u1", B, H, W, extra_res=x0, want_act=True)
+        else:
+            s_raw, s_act = x0, x0_act
+        o, _ = self._rcu(s_raw, s_act, name + "u2", B, H, W)
+        o = ops.gemm(o, self.w[name + "out.w"], bias=self.w[name + "out.b"], out=self._e((B * H * W, F_), hf))
+        return ops.upsample_bilinear(o, self._e((B * Ho * Wo, F_), hf), B=B, Hi=H, Wi=W, Ho=Ho, Wo=Wo, C_=F_)
+
+    def _dpt(self, feats, V, Hp, Wp):
+        cfg, w = self.cfg, self.w
+        hf = torch.float16
+        C = list(cfg.dpt_out_channels)
+        F_ = cfg.dpt_features
+        n = V * Hp * Wp
+        proj = [ops.gemm(feats[i], w[f"dpt.proj{i}.w"], bias=w[f"dpt.proj{i}.b"], out=self._e((n, C[i]), hf))
+                for i in range(4)]
+        # resize to the 4 pyramid levels (layers/dpt.py:195-213)
+        t0 = ops.gemm(proj[0], w["dpt.up0.w"], bias=w["dpt.up0.b"], out=self._e((n, 16 * C[0]), hf))
+        r0 = ops.pixel_shuffle(t0, self._e((V * 16 * Hp * Wp, C[0]), hf), B=V, h=Hp, w=Wp, s=4, C_=C[0])
+        t1 = ops.gemm(proj[1], w["dpt.up1.w"], bias=w["dpt.up1.b"], out=self._e((n, 4 * C[1]), hf))
+        r1 = ops.pixel_shuffle(t1, self._e((V * 4 * Hp * Wp, C[1]), hf), B=V, h=Hp, w=Wp, s=2, C_=C[1])
+        r2 = proj[2]
+        H3, W3 = (Hp + 1) // 2, (Wp + 1) // 2
+        col = ops.im2col_s2(proj[3], self._e((V * H3 * W3, 9 * C[3]), hf), B=V, H=Hp, W=Wp, C_=C[3])
+        r3 = ops.gemm(col, w["dpt.down3.w"], bias=w["dpt.down3.b"], out=self._e((V * H3 * W3, C[3]), hf))
+        dims = [(4 * Hp, 4 * Wp), (2 * Hp, 2 * Wp), (Hp, Wp), (H3, W3)]
+        lraw, lact = [], []
+        for i, (r, (H, W)) in enumerate(zip((r0, r1, r2, r3), dims)):
+            raw, act = self._e((V * H * W, F_), hf), self._e((V * H * W, F_), hf)
+            self._conv(r, f"dpt.rn{i}", V, H, W, C[i], out=raw, out_act=act)
+            lraw.append(raw), lact.append(act)
+        p4 = self._fusion(4, V, *dims[3], *dims[2], lraw[3], x0_act=lact[3])
+        p3 = self._fusion(3, V, *dims[2], *dims[1], p4, lraw[2], lact[2])
+        p2 = self._fusion(2, V, *dims[1], *dims[0], p3, lraw[1], lact[1])
+        Ho, Wo = 8 * Hp, 8 * Wp
+        p1 = self._fusion(1, V, *dims[0], Ho, Wo, p2, lraw[0], lact[0])
+        # head (layers/dpt.py:266-271); F.interpolate to (8*Hp, 8*Wp) is the identity here (E2)
+        o1 = self._conv(p1, "dpt.oc1", V, Ho, Wo, F_, bias=w["dpt.oc1.b"], out=self._e((V * Ho * Wo, F_ // 2), hf))
+        img = self._e((V, Ho, Wo, 3), torch.float32)
+        self._conv(o1, "dpt.oc2", V, Ho, Wo, F_ // 2, bias=w["dpt.oc2.b"], epi=L.EPI_FINAL, w2=w["dpt.oc3.w"],
+                   b2=w["dpt.oc3.b"], out=img, ldo=3)
+        return img

@@ -1,0 +1,163 @@
+"""Drop-in model object: reference parameter tree + B200 engine.
+
+`RenderFormer` keeps the reference's constructor, state_dict keys,
+`from_pretrained` / `save_pretrained` contract (config.json + model.safetensors, as written by
+the reference's PyTorchModelHubMixin, models/renderformer.py:13) and `forward` signature
+(models/renderformer.py:171), but the forward pass runs on renderformer_b200.engine.Engine.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from .config import RenderFormerConfig
+from .engine import Engine, SceneState
+from .synth import state_dict_shapes
+
+
+class _Params(nn.Module):
+    """A parameter container addressed by dotted state_dict keys."""
+
+    def add(self, dotted: str, shape, trainable: bool = True) -> None:
+        mod = self
+        *path, leaf = dotted.split(".")
+        for name in path:
+            if name not in mod._modules:
+                mod.add_module(name, _Params())
+            mod = mod._modules[name]
+        mod.register_parameter(leaf, nn.Parameter(torch.zeros(shape), requires_grad=trainable))
+
+
+class RenderFormer(_Params):
+    def __init__(self, config: RenderFormerConfig):
+        super().__init__()
+        if isinstance(config, dict):
+            config = RenderFormerConfig.from_dict(config)
+        self.config = config
+        for key, shape in state_dict_shapes(config).items():
+            self.add(key, shape, trainable=not key.endswith("rope_emb.freqs"))
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+        self.reset_parameters()
+
+    def reset_parameters(self, seed: int = 0) -> None:
+        from .synth import init_state_dict
+        self.load_state_dict(init_state_dict(self.config, seed))
+
+    # ---- persistence (same files as the reference's hub mixin) ----------------------
+    @classmethod
+    def from_pretrained(cls, model_id: str, **_) -> "RenderFormer":
+        path = model_id
+        if not os.path.isdir(path):
+            from huggingface_hub import snapshot_download  # needs network; not used in tests
+            path = snapshot_download(model_id)
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = RenderFormerConfig.from_dict(json.load(f))
+        model = cls(cfg)
+        from safetensors.torch import load_file
+        model.load_state_dict(load_file(os.path.join(path, "model.safetensors")), strict=True)
+        return model
+
+    def save_pretrained(self, path: str) -> None:
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(self.config.to_dict(), f, indent=2)
+        from safetensors.torch import save_file
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(path, "model.safetensors"))
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    # ---- engine -------------------------------------------------------------------
+    def engine(self) -> Engine:
+        """Kernel-ready weight layouts, cached per (device, parameter versions)."""
+        key = (str(self.device), tuple(p._version for p in self.parameters()))
+        if self._engine is None or self._engine_key != key:
+            self._engine = Engine(self.config, self.state_dict(), self.device)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, tri_vpos_list, texture_patch_list, valid_mask, vns, rays_o=None, rays_d=None,
+                tri_vpos_view_tf=None, tf32_view_tf: bool = False, *, c2w=None, fov=None, resolution=None):
+        """Reference signature (models/renderformer.py:171-206).  The view stage needs the cameras:
+        pass `c2w` [B,V,4,4], `fov` [B,V,1] (degrees) and `resolution` -- the ray map and the
+        camera-space triangles are then rebuilt on the device, so `rays_o`, `rays_d` and
+        `tri_vpos_view_tf` may be None.  Returns log-encoded images [B, V, 3, H, W] like the
+        reference; the pipeline calls the engine directly and skips this round trip."""
+        if c2w is None or fov is None or resolution is None:
+            raise NotImplementedError("RenderFormer.forward needs c2w/fov/resolution keyword arguments; "
+                                      "use RenderFormerRenderingPipeline.render for the reference call surface")
+        eng = self.engine()
+        B = c2w.shape[0]
+        st = eng.encode_scene(tri_vpos_list, texture_patch_list, valid_mask, vns, texture_is_log=True)
+        out = [eng.render_views(st, b, c2w[b], fov[b], resolution) for b in range(B)]
+        hdr = torch.stack(out, dim=0)  # [B,V,H,W,3]
+        return torch.log10(hdr + 1.0).permute(0, 1, 4, 2, 3)
+
+
+class RenderFormerRenderingPipeline:
+    """Same call surface as pipelines/rendering_pipeline.py:8-128."""
+
+    def __init__(self, model: RenderFormer):
+        self.model = model
+        self.config = model.config
+        self.ray_generator = None  # rays are generated inside the fused ray-token kernel
+        self.view_chunk = 8
+
+    @classmethod
+    def from_pretrained(cls, model_id: str):
+        model = RenderFormer.from_pretrained(model_id)
+        model.eval()
+        return cls(model)
+
+    @property
+    def device(self):
+        return self.model.device
+
+    def to(self, device):
+        self.model.to(device)
+
+    @torch.no_grad()
+    def encode(self, triangles, texture, mask, vn) -> SceneState:
+        """View-independent stage only (exposed for multi-GPU view sharding)."""
+        return self.model.engine().encode_scene(triangles, texture, mask, vn)
+
+    @torch.no_grad()
+    def render_views(self, state: SceneState, c2w, fov, resolution: int = 512) -> torch.Tensor:
+        eng = self.model.engine()
+        B, V = c2w.shape[:2]
+        out = []
+        for b in range(B):
+            chunks = [eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
+                                       resolution) for v0 in range(0, V, self.view_chunk)]
+            out.append(torch.cat(chunks, dim=0) if len(chunks) > 1 else chunks[0])
+        return torch.stack(out, dim=0)
+
+    @torch.no_grad()
+    def render(self, triangles, texture, mask, vn, c2w, fov, resolution: int = 512,
+               torch_dtype: torch.dtype = torch.float16):
+        """triangles [B,N,3,3], texture [B,N,13,32,32], mask [B,N] bool, vn [B,N,3,3], c2w [B,V,4,4],
+        fov [B,V,1] degrees -> HDR [B,V,H,W,3] fp32.
+
+        `torch_dtype` is accepted for source compatibility and validated like the reference
+        (rendering_pipeline.py:98); the engine has a single precision policy (bf16/fp16 tensor-core
+        operands, fp32 accumulation) and always returns fp32.  Unlike the reference (:68) the
+        caller's `texture` is not modified."""
+        assert torch_dtype in (torch.bfloat16, torch.float16, torch.float32), \
+            f"Invalid precision: {torch_dtype}\nChoose from: torch.bfloat16, torch.float16, torch.float32"
+        state = self.encode(triangles, texture, mask, vn)
+        return self.render_views(state, c2w, fov, resolution)
+
+    def __call__(self, *args, **kwargs):
+        return self.render(*args, **kwargs)

@@ -1,0 +1,170 @@
+"""Torch-tensor front-ends of the C-ABI kernels (pointer + shape marshalling only, no math).
+
+Every function launches on the current CUDA stream and writes into caller-provided (or
+freshly `torch.empty`-allocated) buffers.  dtype mapping: fp32 <-> RFB_F32, bf16 <-> RFB_BF16,
+fp16 <-> RFB_F16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.RfbError("renderformer_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *, M=None, N=None, K=None,
+         bias=None, res1=None, res2=None, out_act=None, row_map=None, epi=L.EPI_STORE, out_dtype=None,
+         conv=None, w2=None, b2=None, lda=None, ldw=None, ldo=None, ldres=None, bn=0) -> torch.Tensor:
+    """out[M,N] = A[M,K] @ W[N,K]^T with fused epilogue.  `conv=(B,H,W,Cin)` switches A to NHWC 3x3
+    implicit GEMM.  Shapes default to the tensors' 2-D shapes."""
+    _need_cuda(A, W)
+    lib = L.load()
+    a = L.GemmArgs()
+    if conv is not None:
+        Bc, Hc, Wc, Cin = conv
+        a.a_mode, a.B, a.H, a.Wd, a.Cin = L.A_CONV3X3, Bc, Hc, Wc, Cin
+        M = Bc * Hc * Wc if M is None else M
+        K = 9 * Cin if K is None else K
+        lda = Cin
+    else:
+        M = A.shape[0] if M is None else M
+        K = A.shape[-1] if K is None else K
+        lda = A.stride(0) if lda is None else lda
+    N = W.shape[0] if N is None else N
+    ldw = W.stride(0) if ldw is None else ldw
+    a.M, a.N, a.K, a.A, a.lda, a.W, a.ldw = M, N, K, A.data_ptr(), lda, W.data_ptr(), ldw
+    a.dtype = _DT[A.dtype]
+    assert W.dtype == A.dtype, "operand dtypes differ"
+    a.epi = epi
+    if out is None and out_act is None:
+        ncols = N // 2 if epi == L.EPI_SWIGLU else (3 if epi == L.EPI_FINAL else N)
+        out = torch.empty((M, ncols), dtype=out_dtype or torch.float32, device=A.device)
+    ref = out if out is not None else out_act
+    a.out, a.out_act = _p(out), _p(out_act)
+    a.out_dtype = _DT[ref.dtype]
+    a.ldo = (ref.stride(0) if ref.dim() == 2 else ref.shape[-1]) if ldo is None else ldo
+    a.bias = _p(bias)
+    if res1 is not None:
+        a.res1, a.res_dtype = res1.data_ptr(), _DT[res1.dtype]
+        a.ldres = (res1.stride(0) if res1.dim() == 2 else res1.shape[-1]) if ldres is None else ldres
+    if res2 is not None:
+        a.res2 = res2.data_ptr()
+    a.row_map = _p(row_map)
+    a.w2, a.b2 = _p(w2), _p(b2)
+    a.bn_override = bn
+    L.check(lib.rfb_gemm(C.byref(a), _stream()), "rfb_gemm")
+    return out if out is not None else out_act
+
+
+def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0, vt_bs=0, o_bs=0,
+              mask_bits=None, mask_bs=0, mode=0, group_id=None, group_period=0, scale=None):
+    _need_cuda(Q, K, Vt, O)
+    lib = L.load()
+    a = L.AttnArgs()
+    a.B, a.H, a.Nq, a.Nk = B, H, Nq, Nk
+    a.Q, a.ldq, a.q_batch_stride = Q.data_ptr(), ldq, q_bs
+    a.K, a.ldk, a.k_batch_stride = K.data_ptr(), ldk, k_bs
+    a.Vt, a.ldvt, a.vt_batch_stride = Vt.data_ptr(), ldvt, vt_bs
+    a.O, a.ldo, a.o_batch_stride = O.data_ptr(), ldo, o_bs
+    a.key_mask_bits, a.mask_batch_stride_words = _p(mask_bits), mask_bs
+    a.mode, a.group_id, a.group_period = mode, _p(group_id), group_period
+    a.scale = scale if scale is not None else 128 ** -0.5
+    L.check(lib.rfb_attention(C.byref(a), _stream()), "rfb_attention")
+    return O
+
+
+def rmsnorm(x, w, out, *, rows, d, eps=1e-6, gather=None, ldx=None, ldo=None):
+    _need_cuda(x, w, out)
+    L.check(L.load().rfb_rmsnorm(x.data_ptr(), ldx or d, w.data_ptr(), out.data_ptr(), _DT[out.dtype],
+                                 ldo or d, rows, d, eps, _p(gather), _stream()), "rfb_rmsnorm")
+    return out
+
+
+def qknorm_rope(x, w, out, *, rows, d, nseg, ldx, ldo, in_period=0, pos=None, freqs=None, eps=1e-6):
+    _need_cuda(x, w, out)
+    nf = 0 if freqs is None else freqs.numel()
+    L.check(L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), ldo, rows, d,
+                                     nseg, eps, _p(pos), _p(freqs), nf, _stream()), "rfb_qknorm_rope")
+    return out
+
+
+def token_assemble(a, wa, b, wb, token, prefix, out, *, n_prefix, rows_in, rows_out, batch, d):
+    _need_cuda(a, out)
+    L.check(L.load().rfb_token_assemble(a.data_ptr(), wa.data_ptr(), _p(b), _p(wb), token.data_ptr(), _p(prefix),
+                                        n_prefix, out.data_ptr(), rows_in, rows_out, batch, d, _stream()),
+            "rfb_token_assemble")
+    return out
+
+
+def texture_prep(tex, out, *, n_tris, channels, texels, log_channels=3):
+    _need_cuda(tex, out)
+    L.check(L.load().rfb_texture_prep(tex.data_ptr(), out.data_ptr(), n_tris, channels, texels, log_channels,
+                                      _stream()), "rfb_texture_prep")
+    return out
+
+
+def vn_encode(vn, out, *, n, nfreq, ld):
+    _need_cuda(vn, out)
+    L.check(L.load().rfb_vn_encode(vn.data_ptr(), out.data_ptr(), n, nfreq, ld, _stream()), "rfb_vn_encode")
+    return out
+
+
+def ray_tokens(fov_deg, out, *, n_views, resolution):
+    _need_cuda(fov_deg, out)
+    L.check(L.load().rfb_ray_tokens(fov_deg.data_ptr(), out.data_ptr(), n_views, resolution, _stream()),
+            "rfb_ray_tokens")
+    return out
+
+
+def positions(tri, mask_u8, c2w, pos, *, n, n_reg, rows_out, n_views):
+    _need_cuda(tri, mask_u8, pos)
+    L.check(L.load().rfb_positions(tri.data_ptr(), mask_u8.data_ptr(), _p(c2w), pos.data_ptr(), n, n_reg, rows_out,
+                                   n_views, _stream()), "rfb_positions")
+    return pos
+
+
+def pack_mask(mask_u8, bits, *, n, n_prefix, words, batch):
+    _need_cuda(mask_u8, bits)
+    L.check(L.load().rfb_pack_mask(mask_u8.data_ptr(), bits.data_ptr(), n, n_prefix, words, batch, _stream()),
+            "rfb_pack_mask")
+    return bits
+
+
+def cast(x, out):
+    _need_cuda(x, out)
+    L.check(L.load().rfb_cast(x.data_ptr(), out.data_ptr(), _DT[out.dtype], x.numel(), _stream()), "rfb_cast")
+    return out
+
+
+def pixel_shuffle(x, out, *, B, h, w, s, C_):
+    L.check(L.load().rfb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, h, w, s, C_, _stream()), "rfb_pixel_shuffle")
+    return out
+
+
+def im2col_s2(x, out, *, B, H, W, C_):
+    L.check(L.load().rfb_im2col_s2(x.data_ptr(), out.data_ptr(), B, H, W, C_, _stream()), "rfb_im2col_s2")
+    return out
+
+
+def upsample_bilinear(x, out, *, B, Hi, Wi, Ho, Wo, C_):
+    L.check(L.load().rfb_upsample_bilinear(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C_, _stream()),
+            "rfb_upsample_bilinear")
+    return out
