@@ -232,6 +232,19 @@ class Engine:
             v_t.append(vt)
         return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
 
+    def alloc_scene_state(self, B: int, N: int) -> SceneState:
+        """Uninitialised SceneState of the right shapes (receive buffers for the NCCL broadcast)."""
+        cfg = self.cfg
+        d, dv = cfg.latent_dim, cfg.view_transformer_latent_dim
+        Nt = N + cfg.num_register_tokens
+        Ntp = _rup(Nt, 8)
+        words = 4 * ((Ntp + 127) // 128)
+        Lv = cfg.view_transformer_n_layers
+        return SceneState(B, N, Nt, Ntp, self._e((B, Ntp, d), torch.float32), self._e((B, N, 9), torch.float32),
+                          self._e((B, N), torch.uint8), self._e((B, words), torch.int32),
+                          [self._e((B, Ntp, dv), torch.float32) for _ in range(Lv)],
+                          [self._e((B, dv, Ntp), torch.bfloat16) for _ in range(Lv)])
+
     # ------------------------------------------------------------------ stage 2
     def _swin_maps(self, Hp, Wp, shift, V):
         key = (Hp, Wp, shift, V)

@@ -16,6 +16,22 @@ from . import lib as L
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
 
 
+# Optional per-launch timing (bench.py's roofline): a list that receives
+# (kernel family, algorithmic flops, start event, end event) for the tensor-core launches.
+PROFILE = None
+
+
+def _timed(kind: str, flops: float, launch, tag: str = ""):
+    if PROFILE is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = launch()
+    e1.record()
+    PROFILE.append((kind, flops, e0, e1, tag))
+    return rc
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -70,7 +86,8 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
     a.row_map = _p(row_map)
     a.w2, a.b2 = _p(w2), _p(b2)
     a.bn_override = bn
-    L.check(lib.rfb_gemm(C.byref(a), _stream()), "rfb_gemm")
+    tag = f"M={M} N={N} K={K} epi={epi} conv={int(conv is not None)} out={a.out_dtype} res={int(res1 is not None)}"
+    L.check(_timed("gemm", 2.0 * M * N * K, lambda: lib.rfb_gemm(C.byref(a), _stream()), tag), "rfb_gemm")
     return out if out is not None else out_act
 
 
@@ -87,84 +104,82 @@ def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0,
     a.key_mask_bits, a.mask_batch_stride_words = _p(mask_bits), mask_bs
     a.mode, a.group_id, a.group_period = mode, _p(group_id), group_period
     a.scale = scale if scale is not None else 128 ** -0.5
-    L.check(lib.rfb_attention(C.byref(a), _stream()), "rfb_attention")
+    keys = 128 if mode == 1 else Nk
+    L.check(_timed("attention", 4.0 * B * H * Nq * keys * 128, lambda: lib.rfb_attention(C.byref(a), _stream()),
+                   f"B={B} H={H} Nq={Nq} Nk={Nk} mode={mode}"), "rfb_attention")
     return O
 
 
 def rmsnorm(x, w, out, *, rows, d, eps=1e-6, gather=None, ldx=None, ldo=None):
     _need_cuda(x, w, out)
-    L.check(L.load().rfb_rmsnorm(x.data_ptr(), ldx or d, w.data_ptr(), out.data_ptr(), _DT[out.dtype],
-                                 ldo or d, rows, d, eps, _p(gather), _stream()), "rfb_rmsnorm")
+    L.check(_timed("rmsnorm", 0.0, lambda: L.load().rfb_rmsnorm(x.data_ptr(), ldx or d, w.data_ptr(), out.data_ptr(), _DT[out.dtype],
+                                 ldo or d, rows, d, eps, _p(gather), _stream())), "rfb_rmsnorm")
     return out
 
 
 def qknorm_rope(x, w, out, *, rows, d, nseg, ldx, ldo, in_period=0, pos=None, freqs=None, eps=1e-6):
     _need_cuda(x, w, out)
     nf = 0 if freqs is None else freqs.numel()
-    L.check(L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), ldo, rows, d,
-                                     nseg, eps, _p(pos), _p(freqs), nf, _stream()), "rfb_qknorm_rope")
+    L.check(_timed("qknorm_rope", 0.0, lambda: L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), ldo, rows, d,
+                                     nseg, eps, _p(pos), _p(freqs), nf, _stream())), "rfb_qknorm_rope")
     return out
 
 
 def token_assemble(a, wa, b, wb, token, prefix, out, *, n_prefix, rows_in, rows_out, batch, d):
     _need_cuda(a, out)
-    L.check(L.load().rfb_token_assemble(a.data_ptr(), wa.data_ptr(), _p(b), _p(wb), token.data_ptr(), _p(prefix),
-                                        n_prefix, out.data_ptr(), rows_in, rows_out, batch, d, _stream()),
-            "rfb_token_assemble")
+    L.check(_timed("token_assemble", 0.0, lambda: L.load().rfb_token_assemble(a.data_ptr(), wa.data_ptr(), _p(b), _p(wb), token.data_ptr(), _p(prefix),
+                                        n_prefix, out.data_ptr(), rows_in, rows_out, batch, d, _stream())), "rfb_token_assemble")
     return out
 
 
 def texture_prep(tex, out, *, n_tris, channels, texels, log_channels=3):
     _need_cuda(tex, out)
-    L.check(L.load().rfb_texture_prep(tex.data_ptr(), out.data_ptr(), n_tris, channels, texels, log_channels,
-                                      _stream()), "rfb_texture_prep")
+    L.check(_timed("texture_prep", 0.0, lambda: L.load().rfb_texture_prep(tex.data_ptr(), out.data_ptr(), n_tris, channels, texels, log_channels,
+                                      _stream())), "rfb_texture_prep")
     return out
 
 
 def vn_encode(vn, out, *, n, nfreq, ld):
     _need_cuda(vn, out)
-    L.check(L.load().rfb_vn_encode(vn.data_ptr(), out.data_ptr(), n, nfreq, ld, _stream()), "rfb_vn_encode")
+    L.check(_timed("vn_encode", 0.0, lambda: L.load().rfb_vn_encode(vn.data_ptr(), out.data_ptr(), n, nfreq, ld, _stream())), "rfb_vn_encode")
     return out
 
 
 def ray_tokens(fov_deg, out, *, n_views, resolution):
     _need_cuda(fov_deg, out)
-    L.check(L.load().rfb_ray_tokens(fov_deg.data_ptr(), out.data_ptr(), n_views, resolution, _stream()),
-            "rfb_ray_tokens")
+    L.check(_timed("ray_tokens", 0.0, lambda: L.load().rfb_ray_tokens(fov_deg.data_ptr(), out.data_ptr(), n_views, resolution, _stream())), "rfb_ray_tokens")
     return out
 
 
 def positions(tri, mask_u8, c2w, pos, *, n, n_reg, rows_out, n_views):
     _need_cuda(tri, mask_u8, pos)
-    L.check(L.load().rfb_positions(tri.data_ptr(), mask_u8.data_ptr(), _p(c2w), pos.data_ptr(), n, n_reg, rows_out,
-                                   n_views, _stream()), "rfb_positions")
+    L.check(_timed("positions", 0.0, lambda: L.load().rfb_positions(tri.data_ptr(), mask_u8.data_ptr(), _p(c2w), pos.data_ptr(), n, n_reg, rows_out,
+                                   n_views, _stream())), "rfb_positions")
     return pos
 
 
 def pack_mask(mask_u8, bits, *, n, n_prefix, words, batch):
     _need_cuda(mask_u8, bits)
-    L.check(L.load().rfb_pack_mask(mask_u8.data_ptr(), bits.data_ptr(), n, n_prefix, words, batch, _stream()),
-            "rfb_pack_mask")
+    L.check(_timed("pack_mask", 0.0, lambda: L.load().rfb_pack_mask(mask_u8.data_ptr(), bits.data_ptr(), n, n_prefix, words, batch, _stream())), "rfb_pack_mask")
     return bits
 
 
 def cast(x, out):
     _need_cuda(x, out)
-    L.check(L.load().rfb_cast(x.data_ptr(), out.data_ptr(), _DT[out.dtype], x.numel(), _stream()), "rfb_cast")
+    L.check(_timed("cast", 0.0, lambda: L.load().rfb_cast(x.data_ptr(), out.data_ptr(), _DT[out.dtype], x.numel(), _stream())), "rfb_cast")
     return out
 
 
 def pixel_shuffle(x, out, *, B, h, w, s, C_):
-    L.check(L.load().rfb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, h, w, s, C_, _stream()), "rfb_pixel_shuffle")
+    L.check(_timed("pixel_shuffle", 0.0, lambda: L.load().rfb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, h, w, s, C_, _stream())), "rfb_pixel_shuffle")
     return out
 
 
 def im2col_s2(x, out, *, B, H, W, C_):
-    L.check(L.load().rfb_im2col_s2(x.data_ptr(), out.data_ptr(), B, H, W, C_, _stream()), "rfb_im2col_s2")
+    L.check(_timed("im2col_s2", 0.0, lambda: L.load().rfb_im2col_s2(x.data_ptr(), out.data_ptr(), B, H, W, C_, _stream())), "rfb_im2col_s2")
     return out
 
 
 def upsample_bilinear(x, out, *, B, Hi, Wi, Ho, Wo, C_):
-    L.check(L.load().rfb_upsample_bilinear(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C_, _stream()),
-            "rfb_upsample_bilinear")
+    L.check(_timed("upsample_bilinear", 0.0, lambda: L.load().rfb_upsample_bilinear(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C_, _stream())), "rfb_upsample_bilinear")
     return out
