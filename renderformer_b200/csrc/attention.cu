@@ -214,23 +214,33 @@ __global__ void __launch_bounds__(192, 1)
       tc_fence_after();
       const uint32_t ts = tS + sb * 128 + lane_addr;
 
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_wait_ld();
-        if (all_valid) {
+      // the whole 128-column row of S goes to registers in one shot; the TMEM buffer is
+      // released to the MMA warp immediately
+      uint32_t v[4][32];
+      tmem_ld32(ts, v[0]);
+      tmem_ld32(ts + 32, v[1]);
+      tmem_ld32(ts + 64, v[2]);
+      tmem_ld32(ts + 96, v[3]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+
+      if (!all_valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int c = 0; c < 4; ++c) {
           const uint32_t bits = mw[c];
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if ((bits >> i) & 1u) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (!((bits >> i) & 1u)) v[c][i] = 0xff800000u;  // -inf
         }
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_f((m_run - m_use) * sl2);
@@ -242,58 +252,46 @@ __global__ void __launch_bounds__(192, 1)
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + lane_addr + c * 32, v);
+            uint32_t o[32];
+            tmem_ld32(tO + lane_addr + c * 32, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tO + lane_addr + c * 32, v);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + lane_addr + c * 32, o);
           }
           tmem_wait_st();
         }
       }
 
-      // pass 2: P = exp2(s*sl2 - m*sl2) -> bf16 -> swizzled smem
-      float rowsum = 0.f;
-#pragma unroll 1
+      // P = exp2(s*sl2 - m*sl2) -> bf16 -> swizzled smem
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_wait_ld();
-        float pv[32];
-        if (all_valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ex2_f(fmaf(__uint_as_float(v[i]), sl2, neg_ms));
-        } else {
-          const uint32_t bits = mw[c];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            pv[i] = ((bits >> i) & 1u) ? ex2_f(fmaf(__uint_as_float(v[i]), sl2, neg_ms)) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rowsum += pv[i];
         uint8_t* dst = prow + (c >> 1) * kHalfBytes;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          float pv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            pv[e] = ex2_f(fmaf(__uint_as_float(v[c][i * 8 + e]), sl2, neg_ms));
+            rs4[e & 3] += pv[e];
+          }
           uint4 u;
-          u.x = pack_bf16(pv[i * 8 + 0], pv[i * 8 + 1]);
-          u.y = pack_bf16(pv[i * 8 + 2], pv[i * 8 + 3]);
-          u.z = pack_bf16(pv[i * 8 + 4], pv[i * 8 + 5]);
-          u.w = pack_bf16(pv[i * 8 + 6], pv[i * 8 + 7]);
+          u.x = pack_bf16(pv[0], pv[1]);
+          u.y = pack_bf16(pv[2], pv[3]);
+          u.z = pack_bf16(pv[4], pv[5]);
+          u.w = pack_bf16(pv[6], pv[7]);
           const uint32_t chunk = ((c & 1) * 4 + i) ^ rx;
           *reinterpret_cast<uint4*>(dst + chunk * 16) = u;
         }
       }
-      l_run = l_run * alpha + rowsum;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
 
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
     }
 
     // epilogue: O / l -> bf16 -> global

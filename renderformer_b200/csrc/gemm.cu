@@ -2,14 +2,17 @@
 //
 //   C[M,N] = A[M,K] * W[N,K]^T     16-bit operands (bf16 or fp16), fp32 accumulate in TMEM
 //
-// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane,
-// also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> fused math -> HBM).
+// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane,
+// also owns the TMEM allocation), warps 2..9 = epilogue (TMEM -> registers -> fused math -> HBM;
+// two warps per TMEM lane quarter, alternating 32-column chunks).
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop
 // of tile i+1.  A-operand tiles come either from a 2-D tensor map (linear layers) or from a
 // 4-D NHWC tensor map walked over the 9 filter taps (3x3 convolution as implicit GEMM; the
 // zero padding is TMA's out-of-bounds fill, negative coordinates included).
 //
 // Reference call sites replaced: see include/rfb200.h (rfb_gemm).
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "host_util.h"
@@ -39,18 +42,25 @@ struct GemmKParams {
   const float* w2;
   const float* b2;
   int n_store;
+  int direct_store;  // debug: thread-per-row stores instead of the smem-transposed path
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr uint32_t kABytes = kBM * kBK * 2;
 
+// epilogue: 8 warps (two per TMEM lane quarter, alternating 32-column chunks), each with a
+// 32 x 32 fp32 transposition buffer (16-byte chunks XOR-swizzled by row, no padding)
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr uint32_t kEpiStageBytes = kEpiWarps * 32 * 32 * 4;
+
 template <int BN>
 struct GemmCfg {
   static constexpr uint32_t kBBytes = BN * kBK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr uint32_t kSmemBytes = kStages * (kABytes + kBBytes) + 1024 + 256;
+  static constexpr uint32_t kSmemBytes = kStages * (kABytes + kBBytes) + 1024 + 256 + kEpiStageBytes;
 };
 
 __device__ __forceinline__ void load8(const void* base, int dtype, long long idx, float (&x)[8]) {
@@ -158,8 +168,106 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long o
   }
 }
 
+__device__ __forceinline__ void load4(const void* base, int dtype, long long idx, float (&x)[4]) {
+  if (dtype == RFB_F32) {
+    const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + idx);
+    if (dtype == RFB_BF16) {
+      x[0] = __uint_as_float(u.x << 16), x[1] = __uint_as_float(u.x & 0xffff0000u);
+      x[2] = __uint_as_float(u.y << 16), x[3] = __uint_as_float(u.y & 0xffff0000u);
+    } else {
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      x[0] = f0.x, x[1] = f0.y, x[2] = f1.x, x[3] = f1.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store4(void* base, int dtype, long long idx, const float (&x)[4]) {
+  if (dtype == RFB_F32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx) = make_float4(x[0], x[1], x[2], x[3]);
+  } else {
+    uint2 u;
+    if (dtype == RFB_BF16) {
+      u.x = pack_bf16(x[0], x[1]), u.y = pack_bf16(x[2], x[3]);
+    } else {
+      u.x = pack_f16(x[0], x[1]), u.y = pack_f16(x[2], x[3]);
+    }
+    *reinterpret_cast<uint2*>(static_cast<uint16_t*>(base) + idx) = u;
+  }
+}
+
+// RFB_EPI_STORE through a per-warp smem transposition: the accumulator chunk arrives with one
+// thread per row (TMEM lane); it leaves with 8 consecutive lanes covering 128 contiguous bytes
+// of one row, so residual reads and output writes are fully coalesced (4 rows per instruction).
+// The residual loads of the whole chunk are issued up front (before the TMEM load is waited
+// on), so one memory latency is exposed per chunk instead of eight.
+struct EpiRows {
+  int orow[8];
+  bool ok[8];
+  float res[8][4];
+};
+
+__device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane, int orow_mine, bool valid_mine,
+                                                  int n0, EpiRows& e) {
+  const int n = n0 + (lane & 7) * 4;
+  const bool col_ok = n < p.n_store;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    e.orow[it] = __shfl_sync(0xffffffffu, orow_mine, rr);
+    e.ok[it] = (__shfl_sync(0xffffffffu, valid_mine ? 1 : 0, rr) != 0) && col_ok;
+    e.res[it][0] = e.res[it][1] = e.res[it][2] = e.res[it][3] = 0.f;
+  }
+  if (p.res1) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (e.ok[it]) load4(p.res1, p.res_dtype, (long long)e.orow[it] * p.ldres + n, e.res[it]);
+  }
+  if (p.res2) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (e.ok[it]) {
+        float r[4];
+        load4(p.res2, p.res_dtype, (long long)e.orow[it] * p.ldres + n, r);
+        e.res[it][0] += r[0], e.res[it][1] += r[1], e.res[it][2] += r[2], e.res[it][3] += r[3];
+      }
+  }
+}
+
+__device__ __forceinline__ void epilogue_store_coalesced(const GemmKParams& p, float* stage, int lane, int n0,
+                                                         const uint32_t (&v)[32], const EpiRows& e) {
+  const int sw = lane & 7;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ sw) << 2)) =
+        make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                    __uint_as_float(v[g * 4 + 3]));
+  __syncwarp();
+  const int c4 = lane & 7;
+  const int n = n0 + c4 * 4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias && n < p.n_store) load4(p.bias, RFB_F32, n, bias);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+    if (!e.ok[it]) continue;
+    float x[4] = {a.x + bias[0] + e.res[it][0], a.y + bias[1] + e.res[it][1], a.z + bias[2] + e.res[it][2],
+                  a.w + bias[3] + e.res[it][3]};
+    if (p.out) store4(p.out, p.out_dtype, (long long)e.orow[it] * p.ldo + n, x);
+    if (p.out_act) {
+      x[0] = silu_f(x[0]), x[1] = silu_f(x[1]), x[2] = silu_f(x[2]), x[3] = silu_f(x[3]);
+      store4(p.out_act, p.out_dtype, (long long)e.orow[it] * p.ldo + n, x);
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -176,6 +284,7 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,7 +296,7 @@ __global__ void __launch_bounds__(192, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -292,13 +401,22 @@ __global__ void __launch_bounds__(192, 1)
       }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      const bool coalesced = (p.epi == RFB_EPI_STORE) && !p.direct_store;
+      float* my_stage = epi_stage + (warp - 2) * 32 * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {
         if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-        tmem_wait_ld();
-        if (valid) epilogue_chunk(p, orow, n0 + c * 32, v);
+        if (coalesced) {
+          EpiRows e;
+          epilogue_prefetch(p, lane, static_cast<int>(orow), valid, n0 + c * 32, e);
+          tmem_wait_ld();
+          epilogue_store_coalesced(p, my_stage, lane, n0 + c * 32, v, e);
+        } else {
+          tmem_wait_ld();
+          if (valid) epilogue_chunk(p, orow, n0 + c * 32, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -325,7 +443,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
       return RFB_ERR_LAUNCH;
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   g_launch_count++;
   return check_launch("gemm_tc_kernel");
 }
@@ -413,6 +531,14 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   p.num_n_tiles = (a->N + bn - 1) / bn;
   p.idesc = umma_idesc_f16(a->dtype == RFB_BF16 ? 1u : 0u, kBM, bn);
 
+  {
+    static int direct = -1;
+    if (direct < 0) {
+      const char* e = getenv("RFB_EPI_DIRECT");
+      direct = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.direct_store = direct;
+  }
   const long long total = (long long)p.num_m_tiles * p.num_n_tiles;
   int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
   int grid = (int)(total < cap ? total : cap);

@@ -227,6 +227,10 @@ static void bench(const char* name, int M, int N, int K, int epi, int out_dtype,
 }
 
 int main(int argc, char** argv) {
+  if (argc >= 8 && !strcmp(argv[1], "one")) {  // one M N K epi out_dtype bn
+    bench("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    return 0;
+  }
   const bool do_bench = argc > 1 && !strcmp(argv[1], "bench");
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("rfb version %d\n", rfb_version());
