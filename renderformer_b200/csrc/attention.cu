@@ -13,6 +13,8 @@
 // mode 1: block-diagonal -- query tile i only sees key tile i; a tile holds two 64-token swin
 //         windows and tokens attend iff they sit in the same window (tile half) and carry the
 //         same shifted-window region id (layers/attention.py:238-271,327-358).
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "host_util.h"
@@ -21,6 +23,9 @@
 namespace rfb {
 
 extern std::atomic<long long> g_launch_count;
+
+int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                      const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 
 struct AttnKParams {
   int Nq, Nk, H;
@@ -359,6 +364,15 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
     uint64_t dims[3] = {(uint64_t)a->Nk, hd_cols, (uint64_t)(v_batched ? a->B : 1)};
     uint64_t st[2] = {(uint64_t)a->ldvt * 2, (uint64_t)(v_batched ? a->vt_batch_stride : (long long)hd_cols * a->ldvt) * 2};
     if ((rc = make_tmap_16b(&tmV, RFB_BF16, a->Vt, 3, dims, st, box)) != RFB_OK) return rc;
+  }
+
+  if (a->mode == 0) {
+    static int use_v2 = -1;
+    if (use_v2 < 0) {
+      const char* e = getenv("RFB_ATTN_V2");
+      use_v2 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!use_v2) return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
   }
 
   AttnKParams p{};

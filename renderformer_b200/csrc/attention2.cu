@@ -1,0 +1,313 @@
+// Dense flash attention, second generation: two 128-query tiles per CTA sharing one K/V stream,
+// P kept in tensor memory.
+//
+//   warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax of query tile A,
+//   warps 6..9 = softmax of query tile B (one thread per query row).
+//
+// TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512).
+// After the softmax has pulled its whole S row into registers it writes P (bf16 pairs) back into
+// the first 64 columns of the same S region; the P.V product then takes its A operand straight
+// from TMEM (tcgen05.mma with a TMEM A descriptor), so P never touches shared memory and the
+// only smem traffic of the second GEMM is V.  The MMA issue order
+//     PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)
+// lets the tensor pipe work on one query tile while the other tile's softmax runs.  Because
+// tcgen05 operations of one thread complete in order, "S_t(j) is ready" already implies
+// "PV_t(j-1) is done", so the (rare) O rescale needs no extra barrier.
+//
+// Used for mode 0 (encoder self-attention, decoder cross-attention, key-padding mask); the
+// block-diagonal swin mode stays on attn_tc_kernel.  Reference call sites: include/rfb200.h.
+#include <atomic>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace rfb {
+
+extern std::atomic<long long> g_launch_count;
+
+struct Attn2Params {
+  int Nq, Nk, n_kv_tiles;
+  int k_batched, v_batched;
+  const uint32_t* mask_bits;
+  long long mask_stride_words;
+  void* O;
+  long long ldo, o_batch_stride;
+  float scale_log2;
+};
+
+constexpr uint32_t kT2 = 128 * 128 * 2;  // 128 x 128 bf16 tile
+constexpr uint32_t kH2 = 128 * 64 * 2;   // one 64-column swizzle half
+constexpr int kStg = 2;
+constexpr int kAttn2Threads = 64 + 2 * 128;
+constexpr uint32_t kAttn2Smem = kT2 * (2 + 2 * kStg) + 1024 + 256;
+
+__global__ void __launch_bounds__(kAttn2Threads, 1)
+    attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                 // 2 tiles
+  uint8_t* sK = sQ + 2 * kT2;         // kStg tiles
+  uint8_t* sV = sK + kStg * kT2;      // kStg tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStg * kT2);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = q_full + 1;      // kStg
+  uint64_t* k_empty = k_full + kStg;  // kStg
+  uint64_t* v_full = k_empty + kStg;  // kStg
+  uint64_t* v_empty = v_full + kStg;  // kStg
+  uint64_t* s_full = v_empty + kStg;  // 2 (per query tile)
+  uint64_t* p_full = s_full + 2;      // 2
+  uint64_t* o_done = p_full + 2;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 256;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStg; ++i) {
+      mbar_init(&k_full[i], 1), mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1), mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) mbar_init(&s_full[t], 1), mbar_init(&p_full[t], 4), mbar_init(&o_done[t], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ), tma_prefetch_desc(&tmK), tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = p.n_kv_tiles;
+  const int kb = p.k_batched ? b : 0;
+  const int vb = p.v_batched ? b : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * kT2);
+      for (int t = 0; t < 2; ++t) {
+        tma_load_3d(sQ + t * kT2, &tmQ, q_full, h * 128, q0 + t * 128, b);
+        tma_load_3d(sQ + t * kT2 + kH2, &tmQ, q_full, h * 128 + 64, q0 + t * 128, b);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % kStg;
+        const uint32_t ph = (j / kStg) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], kT2);
+        tma_load_3d(sK + s * kT2, &tmK, &k_full[s], h * 128, j * 128, kb);
+        tma_load_3d(sK + s * kT2 + kH2, &tmK, &k_full[s], h * 128 + 64, j * 128, kb);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], kT2);
+        tma_load_3d(sV + s * kT2, &tmV, &v_full[s], j * 128, h * 128, vb);
+        tma_load_3d(sV + s * kT2 + kH2, &tmV, &v_full[s], j * 128 + 64, h * 128, vb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
+      auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T
+        const int s = j % kStg;
+        const uint64_t ad = umma_desc_sw128(smem_u32(sQ + t * kT2));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sK + s * kT2));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * (kH2 >> 4) + (k & 3) * 2;
+          umma_f16(tmem_base + t * 128, ad + off, bd + off, idesc, k != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j   (A operand from TMEM)
+        const int s = j % kStg;
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        const uint64_t bd = umma_desc_sw128(smem_u32(sV + s * kT2));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * (kH2 >> 4) + (k & 3) * 2;
+          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, bd + off, idesc, (j | k) != 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % kStg;
+        const bool more = j + 1 < n_tiles;
+        const int s1 = (j + 1) % kStg;
+        mbar_wait(&v_full[s], (j / kStg) & 1);
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&k_full[s1], ((j + 1) / kStg) & 1);
+          tc_fence_after();
+          issue_qk(0, j + 1);
+        }
+        issue_pv(1, j);
+        umma_commit(&v_empty[s]);
+        if (more) {
+          issue_qk(1, j + 1);
+          umma_commit(&k_empty[s1]);
+        }
+      }
+      umma_commit(&o_done[0]);
+      umma_commit(&o_done[1]);
+    }
+  } else {
+    // ------------------------------ softmax warps ------------------------------
+    const int t = (warp - 2) >> 2;  // query tile of this warp group
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_addr;
+    const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      uint32_t mw[4];
+      if (p.mask_bits) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.mask_bits + static_cast<long long>(b) * p.mask_stride_words + j * 4));
+        mw[0] = u.x, mw[1] = u.y, mw[2] = u.z, mw[3] = u.w;
+      } else {
+        const int rem = p.Nk - j * 128;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int lo = w * 32;
+          mw[w] = rem <= lo ? 0u : (rem - lo >= 32 ? 0xffffffffu : ((1u << (rem - lo)) - 1u));
+        }
+      }
+      const bool all_valid = (mw[0] & mw[1] & mw[2] & mw[3]) == 0xffffffffu;
+
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t v[4][32];
+      tmem_ld32(tS, v[0]);
+      tmem_ld32(tS + 32, v[1]);
+      tmem_ld32(tS + 64, v[2]);
+      tmem_ld32(tS + 96, v[3]);
+      tmem_wait_ld();
+
+      if (!all_valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t bits = mw[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!((bits >> i) & 1u)) v[c][i] = 0xff800000u;  // -inf
+        }
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_f((m_run - m_use) * sl2);
+      const float neg_ms = -m_use * sl2;
+
+      // S_t(j) ready implies PV_t(j-1) retired (in-order tcgen05 pipe): O_t may be rescaled now
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + c * 32, o);
+        }
+      }
+
+      // P = exp2(s*sl2 - m*sl2) -> bf16 pairs -> columns [0,64) of this tile's S region
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_f(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_ms));
+          const float p1 = ex2_f(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_ms));
+          rs4[i & 3] += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      m_run = m_new;
+
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_done[t], 0);
+    tc_fence_after();
+    const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+    const int qrow = q0 + t * 128 + r;
+    const bool row_ok = qrow < p.Nq;
+    uint16_t* orow = static_cast<uint16_t*>(p.O) + static_cast<long long>(b) * p.o_batch_stride +
+                     static_cast<long long>(qrow) * p.ldo + h * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// called by rfb_attention (attention.cu) for mode 0
+int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                      const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream) {
+  Attn2Params p{};
+  p.Nq = a->Nq, p.Nk = a->Nk;
+  p.n_kv_tiles = (a->Nk + 127) / 128;
+  p.k_batched = k_batched, p.v_batched = v_batched;
+  p.mask_bits = a->key_mask_bits;
+  p.mask_stride_words = a->mask_batch_stride_words;
+  p.O = a->O, p.ldo = a->ldo, p.o_batch_stride = a->o_batch_stride;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=
+        cudaSuccess)
+      return RFB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  dim3 grid((a->Nq + 255) / 256, a->H, a->B);
+  attn2_tc_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tmQ, tmK, tmV, p);
+  g_launch_count++;
+  return check_launch("attn2_tc_kernel");
+}
+
+}  // namespace rfb
