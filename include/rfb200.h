@@ -76,6 +76,28 @@ typedef struct {
   const float* b2;    /* RFB_EPI_FINAL: [3] */
   int bn_override;    /* 0 = auto; else force the N tile (32/64/128/256) */
   int max_ctas;       /* 0 = one per SM */
+  /* ---- fused RMSNorm plumbing (RFB_EPI_STORE / RFB_EPI_SWIGLU; all optional) -----------------
+   * RMSNorm(x) W^T = r * (x (W . w)^T), r = rsqrt(mean(x^2) + eps): the norm weight w is folded
+   * into W offline, A is the raw activation in 16 bits, and the per-row factor r is applied to
+   * the accumulator here.  Row sums of squares travel between kernels as PARTIAL sums, one per
+   * RFB_SUMSQ_PART_COLS (128) columns of the producing GEMM: no atomics, no clearing, and the
+   * result is deterministic.  A consumer adds the first `parts` entries of its row. */
+  const float* in_sumsq; /* [M][in_sumsq_ld] partial sums of x^2 of the A rows; r applied per row */
+  int in_sumsq_ld;
+  int in_sumsq_parts;
+  const float* in_rscale; /* ready-made factors instead of in_sumsq: [M] (scale_dim 0) or [N] (scale_dim 1) */
+  int scale_dim;
+  int norm_dim;           /* row length the mean is taken over */
+  float norm_eps;
+  float* out_rscale;      /* [M] side output: the factor r derived from in_sumsq */
+  float* out_sumsq;       /* [rows][out_sumsq_ld]: entry n/128 = sum over columns [128(n/128), +128) of v^2,
+                             v = value stored to out; needs N % 128 == 0 (forces the 256-wide tile) */
+  int out_sumsq_ld;
+  void* out16;            /* extra 16-bit copy of v * col_mul[n] */
+  int out16_dtype;
+  long long ld16;
+  const float* col_mul;   /* [N] or NULL */
+  const int* aux_row_map; /* row of out16 / out_sumsq = aux_row_map ? aux_row_map[out_row] : out_row */
 } rfb_gemm_args;
 
 int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream);
@@ -110,6 +132,16 @@ typedef struct {
                               half of the tile and equal ids */
   int group_period;
   float scale;
+  /* fused QK-RMSNorm (optional): Q / K hold q*w, k*w un-normalised; logits are multiplied by
+   * rsqrt(SQ(q_sumsq, b*Nq+i)/norm_dim + eps) * rsqrt(SQ(k_sumsq, b*Nk+j)/norm_dim + eps) with
+   * SQ(p, r) = sum of p[r*sumsq_ld + 0 .. sumsq_parts) (partial sums left by rfb_gemm's out_sumsq).
+   * k_sumsq: mode 1 only. */
+  const float* q_sumsq;
+  const float* k_sumsq;
+  int sumsq_ld;
+  int sumsq_parts;
+  int norm_dim;
+  float norm_eps;
 } rfb_attn_args;
 
 int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
@@ -123,6 +155,12 @@ int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
  * window_partition (:334-339) into the read.  out_dtype RFB_F32/BF16/F16. */
 int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* out, int out_dtype, long long ldo,
                 int rows, int d, float eps, const int* gather, rfb_stream_t stream);
+
+/* out16[r,:] = cast(x[r,:]) (16-bit), sumsq[r*sumsq_ld] = sum(x[r,:]^2), sumsq[r*sumsq_ld + 1..parts) = 0:
+ * seeds the fused-norm GEMM chain (the input side of nn.RMSNorm, layers/attention.py:503-526,
+ * without materialising norm(x)) in the partial-sum layout rfb_gemm's out_sumsq uses. */
+int rfb_rowstat(const float* x, void* out16, int out_dtype, float* sumsq, int sumsq_ld, int parts, int rows, int d,
+                rfb_stream_t stream);
 
 /* QK-RMSNorm over the full model width + triangle RoPE (layers/attention.py:128-141,
  * encodings/rope.py:78-149,152-206): fp32 [rows, nseg*d] -> bf16.  Input row = r % in_period

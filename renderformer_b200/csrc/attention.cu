@@ -39,12 +39,25 @@ struct AttnKParams {
   void* O;
   long long ldo, o_batch_stride;
   float scale_log2;
+  const float* q_sumsq;
+  const float* k_sumsq;
+  int sumsq_ld, sumsq_parts;
+  float inv_norm_dim, norm_eps;
 };
+
+// 1/rms of one row from its partial sums of squares
+__device__ __forceinline__ float rms_factor(const float* sumsq, long long row, int ld, int parts, float inv_dim,
+                                            float eps) {
+  const float* sp = sumsq + row * ld;
+  float ss = 0.f;
+  for (int j = 0; j < parts; ++j) ss += sp[j];
+  return rsqrtf(ss * inv_dim + eps);
+}
 
 constexpr uint32_t kTileBytes = 128 * 128 * 2;  // one 128 x 128 bf16 operand tile (two SW128 halves)
 constexpr uint32_t kHalfBytes = 128 * 64 * 2;
 constexpr int kKVStages = 2;
-constexpr uint32_t kAttnSmem = kTileBytes * (1 + 2 * kKVStages + 1) + 1024 + 256;
+constexpr uint32_t kAttnSmem = kTileBytes * (1 + 2 * kKVStages + 1) + 1024 + 1024;
 
 __global__ void __launch_bounds__(192, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -68,6 +81,7 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* pv_done = p_full + 1;           // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
   uint8_t* s_gid = reinterpret_cast<uint8_t*>(tmem_slot + 2);  // 128 group ids (mode 1)
+  float* s_rk = reinterpret_cast<float*>(s_gid + 128);          // 128 per-key 1/rms factors (mode 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +107,10 @@ __global__ void __launch_bounds__(192, 1)
   if (p.mode == 1 && threadIdx.x >= 64) {
     const int i = threadIdx.x - 64;
     s_gid[i] = p.group_id[(q0 + i) % p.group_period];
+    float rk = 1.0f;
+    if (p.k_sumsq && q0 + i < p.Nk)
+      rk = rms_factor(p.k_sumsq, q0 + i, p.sumsq_ld, p.sumsq_parts, p.inv_norm_dim, p.norm_eps);
+    s_rk[i] = rk;
   }
   tc_fence_before();
   __syncthreads();
@@ -172,7 +190,10 @@ __global__ void __launch_bounds__(192, 1)
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const float sl2 = p.scale_log2;
+    float sl2 = p.scale_log2;
+    if (p.q_sumsq && q0 + r < p.Nq)
+      sl2 *= rms_factor(p.q_sumsq, static_cast<long long>(b) * p.Nq + q0 + r, p.sumsq_ld, p.sumsq_parts,
+                        p.inv_norm_dim, p.norm_eps);
     float m_run = -INFINITY, l_run = 0.f;
     uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     if (p.mode == 1) {
@@ -231,6 +252,12 @@ __global__ void __launch_bounds__(192, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
 
+      if (p.mode == 1 && p.k_sumsq) {  // fused k RMSNorm: per-key 1/rms
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c][i] = __float_as_uint(__uint_as_float(v[c][i]) * s_rk[c * 32 + i]);
+      }
       if (!all_valid) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -385,6 +412,9 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
   p.group_id = a->group_id, p.group_period = a->group_period;
   p.O = a->O, p.ldo = a->ldo, p.o_batch_stride = a->o_batch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.q_sumsq = a->q_sumsq, p.k_sumsq = a->k_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
+  p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
+  p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -33,6 +33,9 @@ struct Attn2Params {
   void* O;
   long long ldo, o_batch_stride;
   float scale_log2;
+  const float* q_sumsq;
+  int sumsq_ld, sumsq_parts;
+  float inv_norm_dim, norm_eps;
 };
 
 constexpr uint32_t kT2 = 128 * 128 * 2;  // 128 x 128 bf16 tile
@@ -168,7 +171,13 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tS = tmem_base + t * 128 + lane_addr;
     const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
-    const float sl2 = p.scale_log2;
+    float sl2 = p.scale_log2;
+    if (p.q_sumsq && q0 + t * 128 + r < p.Nq) {  // fused q RMSNorm: per-row 1/rms folded into the scale
+      const float* sp = p.q_sumsq + (static_cast<long long>(b) * p.Nq + q0 + t * 128 + r) * p.sumsq_ld;
+      float ss = 0.f;
+      for (int j = 0; j < p.sumsq_parts; ++j) ss += sp[j];
+      sl2 *= rsqrtf(ss * p.inv_norm_dim + p.norm_eps);
+    }
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -297,6 +306,9 @@ int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   p.mask_stride_words = a->mask_batch_stride_words;
   p.O = a->O, p.ldo = a->ldo, p.o_batch_stride = a->o_batch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.q_sumsq = a->q_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
+  p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
+  p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=

@@ -43,6 +43,20 @@ struct GemmKParams {
   const float* b2;
   int n_store;
   int direct_store;  // debug: thread-per-row stores instead of the smem-transposed path
+  // fused RMSNorm plumbing
+  const float* in_sumsq;  // per-row partial sums of squares [M][in_sumsq_ld], first in_sumsq_parts entries
+  int in_sumsq_ld, in_sumsq_parts;
+  const float* in_rscale;  // ready-made factors: per A row (scale_dim 0) or per output column (1)
+  int scale_dim;
+  float inv_norm_dim, norm_eps;
+  float* out_rscale;  // [M] side output of the per-row factor derived from in_sumsq
+  float* out_sumsq;   // [rows][out_sumsq_ld]: entry n/128 = sum of v^2 over that 128-column part
+  int out_sumsq_ld;
+  void* out16;
+  int out16_dtype;
+  long long ld16;
+  const float* col_mul;
+  const int* aux_row_map;
 };
 
 constexpr int kBM = 128;
@@ -105,7 +119,7 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long idx, con
 
 // One thread owns one output row; v = 32 consecutive accumulator columns starting at n0.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long orow, int n0,
-                                               const uint32_t (&v)[32]) {
+                                               const uint32_t (&v)[32], float rs) {
   if (p.epi == RFB_EPI_STORE) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -146,8 +160,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long o
       float h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float gate = __uint_as_float(v[g * 8 + j]);
-        const float up = __uint_as_float(v[16 + g * 8 + j]);
+        const float gate = __uint_as_float(v[g * 8 + j]) * rs;
+        const float up = __uint_as_float(v[16 + g * 8 + j]) * rs;
         h[j] = silu_f(gate) * up;
       }
       store8(p.out, p.out_dtype, orow * p.ldo + (n0 >> 1) + g * 8, h);
@@ -202,43 +216,51 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long idx, con
 // RFB_EPI_STORE through a per-warp smem transposition: the accumulator chunk arrives with one
 // thread per row (TMEM lane); it leaves with 8 consecutive lanes covering 128 contiguous bytes
 // of one row, so residual reads and output writes are fully coalesced (4 rows per instruction).
-// The residual loads of the whole chunk are issued up front (before the TMEM load is waited
-// on), so one memory latency is exposed per chunk instead of eight.
-struct EpiRows {
-  int orow[8];
-  bool ok[8];
-  float res[8][4];
+// Row slot `it` of a lane is tile row it*4 + (lane>>3); the per-row metadata (output row, aux
+// row, 1/rms) lives in the row-owner lane and is fetched with a shuffle where it is needed, so
+// the only per-chunk register arrays are the accumulator and the raw residual bits.
+struct EpiRes {
+  uint4 raw[8];  // fp32 residual: 4 floats; 16-bit residuals: res1 in (x,y), res2 in (z,w)
 };
 
-__device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane, int orow_mine, bool valid_mine,
-                                                  int n0, EpiRows& e) {
+// issue the residual loads of one 32-column chunk (independent of the accumulator)
+__device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane, int orow_mine, int n0, EpiRes& e) {
   const int n = n0 + (lane & 7) * 4;
   const bool col_ok = n < p.n_store;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    e.orow[it] = __shfl_sync(0xffffffffu, orow_mine, rr);
-    e.ok[it] = (__shfl_sync(0xffffffffu, valid_mine ? 1 : 0, rr) != 0) && col_ok;
-    e.res[it][0] = e.res[it][1] = e.res[it][2] = e.res[it][3] = 0.f;
-  }
-  if (p.res1) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it)
-      if (e.ok[it]) load4(p.res1, p.res_dtype, (long long)e.orow[it] * p.ldres + n, e.res[it]);
-  }
-  if (p.res2) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it)
-      if (e.ok[it]) {
-        float r[4];
-        load4(p.res2, p.res_dtype, (long long)e.orow[it] * p.ldres + n, r);
-        e.res[it][0] += r[0], e.res[it][1] += r[1], e.res[it][2] += r[2], e.res[it][3] += r[3];
+    const int orow = __shfl_sync(0xffffffffu, orow_mine, it * 4 + (lane >> 3));
+    e.raw[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (orow >= 0 && col_ok) {
+      const long long idx = (long long)orow * p.ldres + n;
+      if (p.res_dtype == RFB_F32) {
+        e.raw[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.res1) + idx);
+      } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res1) + idx);
+        e.raw[it].x = a.x, e.raw[it].y = a.y;
+        if (p.res2) {
+          const uint2 b = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res2) + idx);
+          e.raw[it].z = b.x, e.raw[it].w = b.y;
+        }
       }
+    }
   }
 }
 
-__device__ __forceinline__ void epilogue_store_coalesced(const GemmKParams& p, float* stage, int lane, int n0,
-                                                         const uint32_t (&v)[32], const EpiRows& e) {
+__device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, float& hi) {
+  if (dtype == RFB_BF16) {
+    lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+    lo = f.x, hi = f.y;
+  }
+}
+
+// Returns (in the row-owner lane) the sum of squares of the stored values of that lane's row
+// over this chunk when p.out_sumsq is set; 0 otherwise.
+__device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, float* stage, int lane, int n0,
+                                                          const uint32_t (&v)[32], int orow_mine, int arow_mine,
+                                                          float rs_mine, const EpiRes& e) {
   const int sw = lane & 7;
 #pragma unroll
   for (int g = 0; g < 8; ++g)
@@ -248,22 +270,63 @@ __device__ __forceinline__ void epilogue_store_coalesced(const GemmKParams& p, f
   __syncwarp();
   const int c4 = lane & 7;
   const int n = n0 + c4 * 4;
+  const bool col_ok = n < p.n_store;
   float bias[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p.bias && n < p.n_store) load4(p.bias, RFB_F32, n, bias);
+  float cs[4] = {1.f, 1.f, 1.f, 1.f};
+  float cm[4] = {1.f, 1.f, 1.f, 1.f};
+  if (col_ok) {
+    if (p.bias) load4(p.bias, RFB_F32, n, bias);
+    if (p.in_rscale && p.scale_dim == 1) load4(p.in_rscale, RFB_F32, n, cs);
+    if (p.col_mul) load4(p.col_mul, RFB_F32, n, cm);
+  }
+  const bool has_res = p.res1 != nullptr;
+  float mysq = 0.f;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + (lane >> 3);
+    const int orow = __shfl_sync(0xffffffffu, orow_mine, rr);
+    const float rs = __shfl_sync(0xffffffffu, rs_mine, rr);
     const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-    if (!e.ok[it]) continue;
-    float x[4] = {a.x + bias[0] + e.res[it][0], a.y + bias[1] + e.res[it][1], a.z + bias[2] + e.res[it][2],
-                  a.w + bias[3] + e.res[it][3]};
-    if (p.out) store4(p.out, p.out_dtype, (long long)e.orow[it] * p.ldo + n, x);
-    if (p.out_act) {
+    float x[4] = {a.x * rs * cs[0] + bias[0], a.y * rs * cs[1] + bias[1], a.z * rs * cs[2] + bias[2],
+                  a.w * rs * cs[3] + bias[3]};
+    if (has_res) {
+      if (p.res_dtype == RFB_F32) {
+        x[0] += __uint_as_float(e.raw[it].x), x[1] += __uint_as_float(e.raw[it].y);
+        x[2] += __uint_as_float(e.raw[it].z), x[3] += __uint_as_float(e.raw[it].w);
+      } else {
+        float r0, r1, r2, r3;
+        unpack16x2(e.raw[it].x, p.res_dtype, r0, r1), unpack16x2(e.raw[it].y, p.res_dtype, r2, r3);
+        x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
+        if (p.res2) {
+          unpack16x2(e.raw[it].z, p.res_dtype, r0, r1), unpack16x2(e.raw[it].w, p.res_dtype, r2, r3);
+          x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
+        }
+      }
+    }
+    const bool ok = orow >= 0 && col_ok;
+    if (ok && p.out) store4(p.out, p.out_dtype, (long long)orow * p.ldo + n, x);
+    if (p.out_sumsq) {  // warp-uniform
+      float s = ok ? x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] : 0.f;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const float t = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);  // row it*4 + (lane&3) -> its owner lane
+      if ((lane >> 2) == it) mysq += t;
+    }
+    if (p.out16) {  // warp-uniform
+      const int arow = __shfl_sync(0xffffffffu, arow_mine, rr);
+      if (ok) {
+        const float y[4] = {x[0] * cm[0], x[1] * cm[1], x[2] * cm[2], x[3] * cm[3]};
+        store4(p.out16, p.out16_dtype, (long long)arow * p.ld16 + n, y);
+      }
+    }
+    if (ok && p.out_act) {
       x[0] = silu_f(x[0]), x[1] = silu_f(x[1]), x[2] = silu_f(x[2]), x[3] = silu_f(x[3]);
-      store4(p.out_act, p.out_dtype, (long long)e.orow[it] * p.ldo + n, x);
+      store4(p.out_act, p.out_dtype, (long long)orow * p.ldo + n, x);
     }
   }
   __syncwarp();
+  return mysq;
 }
 
 template <int BN>
@@ -399,25 +462,64 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         valid = (y < p.H) && (x < p.Wd);
         orow = (static_cast<long long>(bi) * p.H + y) * p.Wd + x;
       }
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
+      // fused-norm inputs of this thread's row: aux row index and 1/rms factor
+      int orow_mine = valid ? static_cast<int>(orow) : -1;
+      int arow_mine = orow_mine;
+      float rs = 1.0f;
+      if (valid) {
+        if (p.aux_row_map) arow_mine = p.aux_row_map[orow];
+        if (p.in_sumsq) {
+          const float* sp = p.in_sumsq + static_cast<long long>(mt * kBM + r) * p.in_sumsq_ld;
+          float ss = 0.f;
+          if (((p.in_sumsq_parts | p.in_sumsq_ld) & 3) == 0) {
+            for (int j = 0; j < p.in_sumsq_parts; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(sp + j);
+              ss += (t.x + t.y) + (t.z + t.w);
+            }
+          } else {
+            for (int j = 0; j < p.in_sumsq_parts; ++j) ss += sp[j];
+          }
+          rs = rsqrtf(ss * p.inv_norm_dim + p.norm_eps);
+          if (p.out_rscale && n0 == 0 && warp < 6) p.out_rscale[mt * kBM + r] = rs;
+        } else if (p.in_rscale && p.scale_dim == 0) {
+          rs = p.in_rscale[mt * kBM + r];
+        }
+      }
       const bool coalesced = (p.epi == RFB_EPI_STORE) && !p.direct_store;
       float* my_stage = epi_stage + (warp - 2) * 32 * 32;
+      // the two warps of a TMEM lane quarter take the two contiguous halves of the tile's columns
+      constexpr int NCH = BN / 32;
+      constexpr int HALF = (NCH + 1) / 2;
+      const int c_begin = ((warp - 2) >> 2) * HALF;
+      const int c_end = (c_begin + HALF < NCH) ? c_begin + HALF : NCH;
+      const bool has_res = coalesced && p.res1 != nullptr;
+      EpiRes cur, nxt;
+      // the first chunk's residual does not depend on the accumulator: fetch it while the
+      // main loop of this tile is still running
+      if (has_res && c_begin < c_end && n0 + c_begin * 32 < p.n_store)
+        epilogue_prefetch(p, lane, orow_mine, n0 + c_begin * 32, cur);
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      float sq = 0.f;
 #pragma unroll 1
-      for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {
+      for (int c = c_begin; c < c_end; ++c) {
         if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
         if (coalesced) {
-          EpiRows e;
-          epilogue_prefetch(p, lane, static_cast<int>(orow), valid, n0 + c * 32, e);
+          if (has_res && c + 1 < c_end && n0 + (c + 1) * 32 < p.n_store)
+            epilogue_prefetch(p, lane, orow_mine, n0 + (c + 1) * 32, nxt);
           tmem_wait_ld();
-          epilogue_store_coalesced(p, my_stage, lane, n0 + c * 32, v, e);
+          sq += epilogue_store_coalesced(p, my_stage, lane, n0 + c * 32, v, orow_mine, arow_mine, rs, cur);
+          cur = nxt;
         } else {
           tmem_wait_ld();
-          if (valid) epilogue_chunk(p, orow, n0 + c * 32, v);
+          if (valid) epilogue_chunk(p, orow, n0 + c * 32, v, rs);
         }
       }
+      // BN == 256 whenever out_sumsq is set: this warp's columns are exactly one 128-column part
+      if (coalesced && p.out_sumsq && valid && n0 + c_begin * 32 < p.n_store)
+        p.out_sumsq[static_cast<long long>(arow_mine) * p.out_sumsq_ld + ((n0 + c_begin * 32) >> 7)] = sq;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -465,7 +567,32 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   p.ldres = a->ldres, p.out = a->out, p.out_dtype = a->out_dtype, p.ldo = a->ldo;
   p.out_act = a->out_act, p.row_map = a->row_map, p.w2 = a->w2, p.b2 = a->b2;
 
+  p.in_sumsq = a->in_sumsq, p.in_sumsq_ld = a->in_sumsq_ld > 0 ? a->in_sumsq_ld : 1;
+  p.in_sumsq_parts = a->in_sumsq_parts > 0 ? a->in_sumsq_parts : 1;
+  p.in_rscale = a->in_rscale, p.scale_dim = a->scale_dim, p.out_rscale = a->out_rscale;
+  p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f;
+  p.norm_eps = a->norm_eps;
+  p.out_sumsq = a->out_sumsq, p.out_sumsq_ld = a->out_sumsq_ld;
+  p.out16 = a->out16, p.out16_dtype = a->out16_dtype, p.ld16 = a->ld16;
+  p.col_mul = a->col_mul, p.aux_row_map = a->aux_row_map;
+  const bool fused_any = a->in_sumsq || a->in_rscale || a->out_rscale || a->out_sumsq || a->out16 || a->col_mul;
+  if (a->in_sumsq && (a->norm_dim <= 0 || a->in_rscale || p.in_sumsq_parts > p.in_sumsq_ld)) return RFB_ERR_ARG;
+  if (a->in_rscale && a->scale_dim != 0 && a->scale_dim != 1) return RFB_ERR_ARG;
+  if (a->out_rscale && !a->in_sumsq) return RFB_ERR_ARG;
+  if (fused_any && a->epi == RFB_EPI_FINAL) return RFB_ERR_ARG;
+  if (a->epi == RFB_EPI_SWIGLU && (a->out_rscale || a->out_sumsq || a->out16 || a->col_mul ||
+                                   (a->in_rscale && a->scale_dim != 0)))
+    return RFB_ERR_ARG;
+  if (a->out16 && (a->ld16 % 8 || (a->out16_dtype != RFB_BF16 && a->out16_dtype != RFB_F16))) return RFB_ERR_ARG;
+  if (a->out16 && a->N % 8) return RFB_ERR_ARG;
+  if (a->out_sumsq && (a->N % 128 || a->out_sumsq_ld < a->N / 128)) return RFB_ERR_ARG;
+  if (a->res2 && (a->res_dtype == RFB_F32 || !a->res1)) return RFB_ERR_ARG;
+
   int bn = a->bn_override;
+  if (a->out_sumsq) {
+    if (bn != 0 && bn != 256) return RFB_ERR_ARG;
+    bn = 256;  // one epilogue warp per 128-column sum-of-squares part
+  }
   if (bn == 0) {
     if (a->N <= 32) bn = 32;
     else if (a->N <= 64) bn = 64;
@@ -478,7 +605,7 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     p.n_store = (a->N + 7) & ~7;
     if (p.n_store > a->ldo) return RFB_ERR_ARG;
     if ((a->bias || a->res1 || a->res2) && (a->N % 8) != 0) return RFB_ERR_ARG;
-    if (!a->out && !a->out_act) return RFB_ERR_ARG;
+    if (!a->out && !a->out_act && !a->out16) return RFB_ERR_ARG;
     const int align = (a->out_dtype == RFB_F32) ? 4 : 8;
     if (a->ldo % align) return RFB_ERR_ALIGN;
     if ((a->res1 || a->res2) && a->ldres % ((a->res_dtype == RFB_F32) ? 4 : 8)) return RFB_ERR_ALIGN;
@@ -539,6 +666,7 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     }
     p.direct_store = direct;
   }
+  if (p.direct_store && fused_any) p.direct_store = 0;
   const long long total = (long long)p.num_m_tiles * p.num_n_tiles;
   int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
   int grid = (int)(total < cap ? total : cap);

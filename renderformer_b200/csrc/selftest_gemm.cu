@@ -188,6 +188,148 @@ static void run_case(const Case& c) {
   }
 }
 
+// fused-RMSNorm plumbing: in_sumsq partial sums / in_rscale (row or column), out_rscale,
+// out_sumsq partial sums, out16 (+col_mul, aux map)
+static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool swiglu, bool use_map, bool with_res,
+                      bool rowmap = false) {
+  std::vector<uint16_t> hA = rand16((size_t)M * K, 5, 1.0f, RFB_BF16), hW = rand16((size_t)N * K, 6, 0.05f, RFB_BF16);
+  DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K);
+  dA.up(hA), dW.up(hW);
+  DevBuf<float> dacc((size_t)M * N);
+  dim3 g((N + 127) / 128, M);
+  ref_linear<<<g, 128>>>(dA.p, K, dW.p, K, dacc.p, M, N, K, 1);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> acc = dacc.down();
+  const float eps = 1e-6f;
+  const int norm_dim = 1024;
+  const int in_parts = 8, in_ld = 8;
+  // row mode: partial sums; column mode: ready-made factors
+  std::vector<float> hparts((size_t)M * in_ld), hscale(scale_dim == 0 ? M : N);
+  for (int m = 0; m < M; ++m) {
+    float tot = 0.f;
+    for (int j = 0; j < in_parts; ++j) {
+      hparts[(size_t)m * in_ld + j] = (100.f + 900.f * (0.5f + 0.5f * hval(9, m * 8 + j))) / in_parts;
+      tot += hparts[(size_t)m * in_ld + j];
+    }
+    if (scale_dim == 0) hscale[m] = 1.0f / sqrtf(tot / norm_dim + eps);
+  }
+  if (scale_dim == 1)
+    for (int n = 0; n < N; ++n) hscale[n] = 0.5f + 0.5f * (0.5f + 0.5f * hval(19, n));
+  std::vector<float> hcm = rand32(N, 10, 1.0f), hres = rand32((size_t)M * N, 12, 1.0f);
+  std::vector<int> hmap(M), hrmap(M);
+  for (int m = 0; m < M; ++m) hmap[m] = (m * 5 + 3) % M;   // permutations when gcd(., M) == 1
+  for (int m = 0; m < M; ++m) hrmap[m] = rowmap ? (m * 3 + 1) % M : m;
+  DevBuf<float> dparts((size_t)M * in_ld), dscale(hscale.size()), dcm(N), dres((size_t)M * N), drs(M);
+  dparts.up(hparts), dscale.up(hscale), dcm.up(hcm), dres.up(hres);
+  drs.fill_byte(0);
+  DevBuf<int> dmap(M), drmap(M);
+  dmap.up(hmap), drmap.up(hrmap);
+  const bool want_sq = !swiglu && (N % 128 == 0);
+  const int nparts = (N + 127) / 128;
+  const int ocols = swiglu ? N / 2 : N;
+  DevBuf<float> dout((size_t)M * ocols), dosq((size_t)M * nparts);
+  DevBuf<uint16_t> do16((size_t)M * ocols), doutb((size_t)M * ocols);
+  dout.fill_byte(0), do16.fill_byte(0), doutb.fill_byte(0);
+  dosq.fill_byte(0x7f);  // every entry must be overwritten
+
+  rfb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = K, a.W = dW.p, a.ldw = K, a.dtype = RFB_BF16;
+  a.norm_dim = norm_dim, a.norm_eps = eps;
+  if (scale_dim == 0) {
+    a.in_sumsq = dparts.p, a.in_sumsq_ld = in_ld, a.in_sumsq_parts = in_parts, a.out_rscale = swiglu ? nullptr : drs.p;
+  } else {
+    a.in_rscale = dscale.p, a.scale_dim = 1;
+  }
+  if (swiglu) {
+    a.epi = RFB_EPI_SWIGLU, a.out = doutb.p, a.out_dtype = RFB_BF16, a.ldo = ocols;
+  } else {
+    a.epi = RFB_EPI_STORE, a.out = dout.p, a.out_dtype = RFB_F32, a.ldo = N;
+    if (with_res) a.res1 = dres.p, a.res_dtype = RFB_F32, a.ldres = N;
+    if (want_sq) a.out_sumsq = dosq.p, a.out_sumsq_ld = nparts;
+    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = dcm.p;
+    a.aux_row_map = use_map ? dmap.p : nullptr;
+    a.row_map = rowmap ? drmap.p : nullptr;
+  }
+  int rc = rfb_gemm(&a, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc != RFB_OK || e != cudaSuccess) {
+    printf("[FAIL] %-46s rc=%d cuda=%s\n", name, rc, cudaGetErrorString(e));
+    g_fail++;
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  auto sc = [&](int m, int n) { return scale_dim == 0 ? hscale[m] : hscale[n]; };
+  if (swiglu) {
+    std::vector<float> exp((size_t)M * ocols);
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; n += 32)
+        for (int j = 0; j < 16; ++j)
+          exp[(size_t)m * ocols + n / 2 + j] =
+              silu_h(acc[(size_t)m * N + n + j] * sc(m, 0)) * (acc[(size_t)m * N + n + 16 + j] * sc(m, 0));
+    report(name, to_float(doutb.p, (size_t)M * ocols, RFB_BF16), exp, 2e-2, 1.2e-2, ocols);
+    return;
+  }
+  std::vector<float> exp((size_t)M * N), exp16((size_t)M * N), expsq((size_t)M * nparts, 0.f);
+  for (int m = 0; m < M; ++m) {
+    const int orow = hrmap[m];
+    const int ar = use_map ? hmap[orow] : orow;
+    for (int n = 0; n < N; ++n) {
+      float v = acc[(size_t)m * N + n] * sc(m, n);
+      if (with_res) v += hres[(size_t)orow * N + n];
+      exp[(size_t)orow * N + n] = v;
+      exp16[(size_t)ar * N + n] = v * hcm[n];
+      expsq[(size_t)ar * nparts + n / 128] += v * v;
+    }
+  }
+  std::string nm(name);
+  report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, N);
+  report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * N, RFB_BF16), exp16, 2e-2, 1.2e-2, N);
+  if (want_sq) report((nm + " [sumsq]").c_str(), dosq.down(), expsq, 1e-2, 2e-3, nparts);
+  if (scale_dim == 0) report((nm + " [rscale]").c_str(), drs.down(), hscale, 1e-5, 1e-4, 1);
+}
+
+// micro-benchmark of the fused residual / projection epilogues at the decoder's shapes
+static void bench_fused(const char* name, int M, int N, int K, bool res, bool sumsq, bool o16, bool in_sq, bool maps,
+                        bool f32out) {
+  DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K), d16((size_t)M * N);
+  CK(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2));
+  CK(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2));
+  DevBuf<float> dx((size_t)M * N), dsq((size_t)M * (N / 128)), dinsq((size_t)M * 8), dcm(N);
+  dx.zero(), dinsq.zero(), dcm.zero();
+  std::vector<int> hmap(M);
+  for (int m = 0; m < M; ++m) hmap[m] = (int)(((long long)m * 8191 + 17) % M);
+  DevBuf<int> dmap(M);
+  dmap.up(hmap);
+  rfb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = K, a.W = dW.p, a.ldw = K, a.dtype = RFB_BF16;
+  a.epi = RFB_EPI_STORE, a.out_dtype = RFB_F32, a.ldo = N;
+  if (f32out) a.out = dx.p;
+  if (res) a.res1 = dx.p, a.res_dtype = RFB_F32, a.ldres = N;
+  if (sumsq) a.out_sumsq = dsq.p, a.out_sumsq_ld = N / 128;
+  if (o16) a.out16 = d16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = dcm.p;
+  if (in_sq) a.in_sumsq = dinsq.p, a.in_sumsq_ld = 8, a.in_sumsq_parts = 8, a.norm_dim = 1024, a.norm_eps = 1e-6f;
+  if (maps) a.row_map = dmap.p;
+  for (int i = 0; i < 3; ++i) {
+    int rc = rfb_gemm(&a, 0);
+    if (rc) {
+      printf("bench %s rc=%d\n", name, rc);
+      return;
+    }
+  }
+  CK(cudaDeviceSynchronize());
+  GpuTimer t;
+  const int iters = 20;
+  t.start();
+  for (int i = 0; i < iters; ++i) rfb_gemm(&a, 0);
+  float ms = t.stop() / iters;
+  CK(cudaDeviceSynchronize());
+  double tf = 2.0 * M * (double)N * K / (ms * 1e-3) / 1e12;
+  printf("[BENCH] %-40s M=%d N=%d K=%d  %.3f ms  %.1f TFLOP/s\n", name, M, N, K, ms, tf);
+  fflush(stdout);
+}
+
 static void bench(const char* name, int M, int N, int K, int epi, int out_dtype, int bn, int conv_hw = 0,
                   int Cin = 0, int batch = 1) {
   const int dtype = conv_hw ? RFB_F16 : RFB_BF16;
@@ -228,7 +370,9 @@ static void bench(const char* name, int M, int N, int K, int epi, int out_dtype,
 
 int main(int argc, char** argv) {
   if (argc >= 8 && !strcmp(argv[1], "one")) {  // one M N K epi out_dtype bn
-    bench("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    // optional: conv_hw Cin batch
+    bench("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]),
+          argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 0, argc > 10 ? atoi(argv[10]) : 1);
     return 0;
   }
   const bool do_bench = argc > 1 && !strcmp(argv[1], "bench");
@@ -258,6 +402,13 @@ int main(int argc, char** argv) {
     };
     int n = quick ? 3 : (int)cases.size();
     for (int i = 0; i < n; ++i) run_case(cases[i]);
+    if (!quick) {
+      run_fused("fused rowscale+sumsq+out16 1031x1024x512", 1031, 1024, 512, 0, false, false, true);
+      run_fused("fused rowscale auxmap 517x512x256", 517, 512, 256, 0, false, true, false);
+      run_fused("fused rowscale rowmap+res 1031x640x256", 1031, 640, 256, 0, false, false, true, true);
+      run_fused("fused colscale 1024x1096x512", 1024, 1096, 512, 1, false, false, false);
+      run_fused("fused swiglu rowscale 777x2048x512", 777, 2048, 512, 0, true, false, false);
+    }
     printf("selftest_gemm: %d failure(s)\n", g_fail);
     if (g_fail) return 1;
   }
@@ -272,6 +423,13 @@ int main(int argc, char** argv) {
       bench("dec 8v q_proj  ", 32768, 1024, 1024, RFB_EPI_STORE, RFB_F32, bn);
       bench("square 8192    ", 8192, 8192, 8192, RFB_EPI_STORE, RFB_BF16, bn);
     }
+    bench_fused("dec wout: res+sumsq+out16 ", 16384, 1024, 1024, true, true, true, false, false, true);
+    bench_fused("dec s.wo: res+sumsq+out16+map", 16384, 1024, 1024, true, true, true, false, true, true);
+    bench_fused("dec w2: res+sumsq+out16 K4096", 16384, 1024, 4096, true, true, true, false, false, true);
+    bench_fused("dec wq: insq+out16+sumsq    ", 16384, 1024, 1024, false, true, true, true, false, false);
+    bench_fused("dec s.wqk: insq+out16+sumsq ", 16384, 2048, 1024, false, true, true, true, false, false);
+    bench_fused("plain res only              ", 16384, 1024, 1024, true, false, false, false, false, true);
+    bench_fused("plain f32 store only        ", 16384, 1024, 1024, false, false, false, false, false, true);
     bench("conv 256^2 128->128", 65536, 128, 1152, RFB_EPI_STORE, RFB_F16, 128, 256, 128);
     bench("conv 512^2 128->64 ", 262144, 64, 1152, RFB_EPI_STORE, RFB_F16, 64, 512, 128);
   }

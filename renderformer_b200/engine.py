@@ -14,6 +14,7 @@ fp16 operands in the token encoders and the DPT head, fp32 accumulation / softma
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -76,6 +77,9 @@ class Engine:
         if self.device.type != "cuda":
             raise L.RfbError("renderformer_b200.Engine needs a CUDA device (there is no CPU fallback)")
         L.load()
+        # fused RMSNorm (norm weights folded into the next GEMM, 1/rms applied in its epilogue from
+        # sums of squares maintained by the residual GEMMs); RFB_UNFUSED=1 keeps the explicit kernels
+        self.fused = os.environ.get("RFB_UNFUSED", "0") != "1"
         self.w: Dict[str, torch.Tensor] = {}
         self._maps: Dict[tuple, tuple] = {}
         self._prepare(state_dict)
@@ -100,6 +104,15 @@ class Engine:
             w = g(k)
             return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
+        fused = self.fused
+
+        def fold(wt, norm_key, on=fused):  # RMSNorm(x) W^T = r * x (W . w)^T : fold the norm weight along K
+            return wt * g(norm_key)[None, :] if on else wt
+
+        # the fused decoder exists for the swin architecture only; the hoisted K/V projections are
+        # part of the (always fused) scene stage
+        fused_dec = self.fused_dec = fused and cfg.view_transformer_use_swin_attn
+
         d = cfg.latent_dim
         put("tri_token", g("tri_token").reshape(-1))
         put("reg_tokens", g("reg_tokens").reshape(cfg.num_register_tokens, d))
@@ -113,12 +126,13 @@ class Engine:
         put("enc.freqs", g("transformer.rope_emb.freqs"))
         for i in range(cfg.num_layers):
             p, o = f"transformer.layers.{i}.", f"enc{i}."
-            w_in = g(p + "multihead_attn.in_proj.weight")
+            w_in = fold(g(p + "multihead_attn.in_proj.weight"), p + "query_norm.weight")
             put(o + "wqk", w_in[: 2 * d], bf), put(o + "wv", w_in[2 * d:], bf)
             put(o + "wo", g(p + "multihead_attn.out_proj.weight"), bf)
             put(o + "qkn", torch.cat([g(p + "multihead_attn.q_norm.weight"), g(p + "multihead_attn.k_norm.weight")]))
             put(o + "n1", g(p + "query_norm.weight")), put(o + "n2", g(p + "ffn_norm.weight"))
-            put(o + "w13", swiglu_w(p + "ffn."), bf), put(o + "w2", g(p + "ffn.w2.weight"), bf)
+            put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight"), bf)
+            put(o + "w2", g(p + "ffn.w2.weight"), bf)
 
         v = "view_transformer."
         dv = cfg.view_transformer_latent_dim
@@ -128,16 +142,19 @@ class Engine:
         put("dec.freqs", g(v + "transformer.rope_emb.freqs"))
         for i in range(cfg.view_transformer_n_layers):
             p, o = v + f"transformer.layers.{i}.", f"dec{i}."
-            for nm in ("q", "k", "v", "out"):
-                put(o + "w" + nm, g(p + f"multihead_attn.{nm}_proj.weight"), bf)
+            put(o + "wq", fold(g(p + "multihead_attn.q_proj.weight"), p + "query_norm.weight", fused_dec), bf)
+            put(o + "wk", fold(g(p + "multihead_attn.k_proj.weight"), p + "kv_norm.weight"), bf)
+            put(o + "wv", fold(g(p + "multihead_attn.v_proj.weight"), p + "kv_norm.weight"), bf)
+            put(o + "wout", g(p + "multihead_attn.out_proj.weight"), bf)
             put(o + "qn", g(p + "multihead_attn.q_norm.weight")), put(o + "kn", g(p + "multihead_attn.k_norm.weight"))
             put(o + "n_q", g(p + "query_norm.weight")), put(o + "n_kv", g(p + "kv_norm.weight"))
-            w_in = g(p + "self_attn.in_proj.weight")
+            w_in = fold(g(p + "self_attn.in_proj.weight"), p + "self_attn_norm.weight", fused_dec)
             put(o + "s.wqk", w_in[: 2 * dv], bf), put(o + "s.wv", w_in[2 * dv:], bf)
             put(o + "s.wo", g(p + "self_attn.out_proj.weight"), bf)
             put(o + "s.qkn", torch.cat([g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight")]))
             put(o + "n_s", g(p + "self_attn_norm.weight")), put(o + "n_f", g(p + "ffn_norm.weight"))
-            put(o + "w13", swiglu_w(p + "ffn."), bf), put(o + "w2", g(p + "ffn.w2.weight"), bf)
+            put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight", fused_dec), bf)
+            put(o + "w2", g(p + "ffn.w2.weight"), bf)
 
         h = v + "out_dpt."
         for i in range(4):
@@ -201,6 +218,9 @@ class Engine:
         words = 4 * ((Ntp + 127) // 128)
         bits = ops.pack_mask(mask_u8, self._e((B, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=B)
 
+        if self.fused:
+            return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8)
+
         # encoder  (layers/attention.py:579-590)
         rows = B * Ntp
         for i in range(cfg.num_layers):
@@ -232,6 +252,48 @@ class Engine:
             v_t.append(vt)
         return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
 
+    def _encode_fused(self, x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8) -> SceneState:
+        """Encoder + K/V hoist with RMSNorm fused into the GEMMs.  State carried between GEMMs:
+        x (fp32 residual), xb (bf16 copy of x), xsq (per-row partial sums of squares of x, one per
+        128 columns)."""
+        cfg, w = self.cfg, self.w
+        d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
+        rows = B * Ntp
+        bf, f32 = torch.bfloat16, torch.float32
+        nrm = dict(norm_dim=d, norm_eps=EPS)
+        P = d // 128
+        xb, xsq = self._e((rows, d), bf), self._e((rows, P), f32)
+        xb2, xsq2 = self._e((rows, d), bf), self._e((rows, P), f32)
+        rsc = self._e((rows,), f32)
+        ops.rowstat(x, xb, xsq, rows=rows, d=d)
+        for i in range(cfg.num_layers):
+            o = f"enc{i}."
+            qk = ops.gemm(xb, w[o + "wqk"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc, **nrm)
+            vt = self._e((B, d, Ntp), bf)
+            for b in range(B):
+                ops.gemm(w[o + "wv"], xb[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp,
+                         in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
+            qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((rows, 2 * d), bf), rows=rows, d=d, nseg=2,
+                                  ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
+            att = self._e((rows, d), bf)
+            ops.attention(qkr, qkr[:, d:], vt, att, B=B, H=H, Nq=Ntp, Nk=Ntp, ldq=2 * d, ldk=2 * d, ldvt=Ntp, ldo=d,
+                          q_bs=Ntp * 2 * d, k_bs=Ntp * 2 * d, vt_bs=d * Ntp, o_bs=Ntp * d, mask_bits=bits,
+                          mask_bs=words)
+            ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2)
+            g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
+            ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
+        k_pre, v_t = [], []
+        for i in range(cfg.view_transformer_n_layers):  # kv_norm is folded into wk / wv
+            o = f"dec{i}."
+            k_pre.append(ops.gemm(xb, w[o + "wk"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc if i == 0 else None,
+                                  **nrm).view(B, Ntp, dv))
+            vt = self._e((B, dv, Ntp), bf)
+            for b in range(B):
+                ops.gemm(w[o + "wv"], xb[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp,
+                         in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
+            v_t.append(vt)
+        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
+
     def alloc_scene_state(self, B: int, N: int) -> SceneState:
         """Uninitialised SceneState of the right shapes (receive buffers for the NCCL broadcast)."""
         cfg = self.cfg
@@ -252,7 +314,10 @@ class Engine:
             perm, region = swin_window_maps(Hp, Wp, shift)
             n = Hp * Wp
             full = (perm[None, :] + (torch.arange(V, dtype=torch.int32) * n)[:, None]).reshape(-1)
-            self._maps[key] = (full.to(self.device).contiguous(), region.to(self.device).contiguous())
+            inv = torch.empty_like(full)
+            inv[full.long()] = torch.arange(full.numel(), dtype=torch.int32)
+            self._maps[key] = (full.to(self.device).contiguous(), region.to(self.device).contiguous(),
+                               inv.to(self.device).contiguous())
         return self._maps[key]
 
     @torch.no_grad()
@@ -282,6 +347,8 @@ class Engine:
         ops.token_assemble(lin, w["ray.norm"], None, None, w["ray.token"], None, x, n_prefix=0, rows_in=rows,
                            rows_out=rows, batch=1, d=dv)
         words = st.mask_bits.shape[1]
+        if self.fused_dec:
+            return self._decode_fused(st, b, x, pos, V, Hp, Wp, taps)
         feats = []
         for i in range(cfg.view_transformer_n_layers):
             o = f"dec{i}."
@@ -299,7 +366,7 @@ class Engine:
 
             # self-attention among ray tokens  (layers/attention.py:515-523)
             if cfg.view_transformer_use_swin_attn:
-                perm, region = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
+                perm, region, _ = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
                 hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS, gather=perm)
                 qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
                 vt = ops.gemm(w[o + "s.wv"], hs, out=self._e((dv, rows), bf), N=rows)
@@ -321,6 +388,56 @@ class Engine:
                               ldo=dv, q_bs=Nr * 2 * dv, k_bs=Nr * 2 * dv, vt_bs=dv * Nrp, o_bs=Nr * dv)
                 ops.gemm(att, w[o + "s.wo"], out=x, res1=x)
             self._ffn(x, rows, dv, w[o + "n_f"], w[o + "w13"], w[o + "w2"])
+            if i in cfg.out_layers:
+                feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
+                if taps is not None:
+                    taps.setdefault("dec_feats", []).append(x.clone().view(V, Nr, dv))
+        return self._dpt(feats, V, Hp, Wp)
+
+    def _decode_fused(self, st: SceneState, b: int, x, pos, V, Hp, Wp, taps):
+        """Swin decoder with RMSNorm / QK-RMSNorm fused into the GEMMs and the attention kernels.
+        Carried state: x fp32 (token order), xb bf16 copy + xsq partial row sums (token order), and
+        their window-order twins xbw / xsqw written by the cross-attention out-projection."""
+        cfg, w = self.cfg, self.w
+        dv, Hh = cfg.view_transformer_latent_dim, cfg.view_transformer_n_heads
+        Nr, Ntp = Hp * Wp, st.Ntp
+        rows = V * Nr
+        bf, f32 = torch.bfloat16, torch.float32
+        nrm = dict(norm_dim=dv, norm_eps=EPS)
+        P = dv // 128
+        xb, xsq = self._e((rows, dv), bf), self._e((rows, P), f32)
+        xbw, xsqw = self._e((rows, dv), bf), self._e((rows, P), f32)
+        qh, qsq = self._e((rows, dv), bf), self._e((rows, P), f32)
+        qkh, qksq = self._e((rows, 2 * dv), bf), self._e((rows, 2 * P), f32)
+        rsw = self._e((rows,), f32)
+        att = self._e((rows, dv), bf)
+        vt = self._e((dv, rows), bf)
+        kbuf = self._e((V * Ntp, dv), bf)
+        ops.rowstat(x, xb, xsq, rows=rows, d=dv)
+        feats = []
+        for i in range(cfg.view_transformer_n_layers):
+            o = f"dec{i}."
+            perm, region, inv = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
+            # cross-attention: q = (n_q(x) Wq^T) . qn / rms  -- the 1/rms goes into the softmax scale
+            ops.gemm(xb, w[o + "wq"], out16=qh, col_mul=w[o + "qn"], out_sumsq=qsq, in_sumsq=xsq, **nrm)
+            ops.qknorm_rope(st.k_pre[i][b], w[o + "kn"], kbuf, rows=V * Ntp, d=dv, nseg=1, ldx=dv, ldo=dv,
+                            in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
+            ops.attention(qh, kbuf, st.v_t[i][b], att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
+                          q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0,
+                          q_sumsq=qsq, sumsq_ld=P, sumsq_parts=P, **nrm)
+            # x += out_proj(att); bf16 copy + row sums land in window order for the swin block
+            ops.gemm(att, w[o + "wout"], out=x, res1=x, out_sumsq=xsqw, out16=xbw, aux_row_map=inv)
+            # shifted-window self-attention (window-major rows); q sums in parts [0,P), k sums in [P,2P)
+            ops.gemm(xbw, w[o + "s.wqk"], out16=qkh, col_mul=w[o + "s.qkn"], out_sumsq=qksq, in_sumsq=xsqw,
+                     out_rscale=rsw, **nrm)
+            ops.gemm(w[o + "s.wv"], xbw, out=vt, N=rows, in_rscale=rsw, scale_dim=1)
+            ops.attention(qkh, qkh[:, dv:], vt, att, B=1, H=Hh, Nq=rows, Nk=rows, ldq=2 * dv, ldk=2 * dv,
+                          ldvt=rows, ldo=dv, mode=1, group_id=region, group_period=Nr,
+                          q_sumsq=qksq, k_sumsq=qksq.view(-1)[P:], sumsq_ld=2 * P, sumsq_parts=P, **nrm)
+            ops.gemm(att, w[o + "s.wo"], out=x, res1=x, row_map=perm, out_sumsq=xsq, out16=xb)
+            # SwiGLU
+            g = ops.gemm(xb, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq, **nrm)
+            ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
             if i in cfg.out_layers:
                 feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
                 if taps is not None:

@@ -38,6 +38,11 @@ class GemmArgs(C.Structure):
         ("out_act", C.c_void_p), ("row_map", C.c_void_p),
         ("w2", C.c_void_p), ("b2", C.c_void_p),
         ("bn_override", C.c_int), ("max_ctas", C.c_int),
+        ("in_sumsq", C.c_void_p), ("in_sumsq_ld", C.c_int), ("in_sumsq_parts", C.c_int),
+        ("in_rscale", C.c_void_p), ("scale_dim", C.c_int), ("norm_dim", C.c_int), ("norm_eps", C.c_float),
+        ("out_rscale", C.c_void_p), ("out_sumsq", C.c_void_p), ("out_sumsq_ld", C.c_int),
+        ("out16", C.c_void_p), ("out16_dtype", C.c_int), ("ld16", C.c_longlong),
+        ("col_mul", C.c_void_p), ("aux_row_map", C.c_void_p),
     ]
 
 
@@ -51,12 +56,15 @@ class AttnArgs(C.Structure):
         ("key_mask_bits", C.c_void_p), ("mask_batch_stride_words", C.c_longlong),
         ("mode", C.c_int), ("group_id", C.c_void_p), ("group_period", C.c_int),
         ("scale", C.c_float),
+        ("q_sumsq", C.c_void_p), ("k_sumsq", C.c_void_p), ("sumsq_ld", C.c_int), ("sumsq_parts", C.c_int),
+        ("norm_dim", C.c_int),
+        ("norm_eps", C.c_float),
     ]
 
 
 # every symbol include/rfb200.h declares (tests/test_abi.py checks the built library exports them)
 SYMBOLS = [
-    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_qknorm_rope",
+    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope",
     "rfb_token_assemble", "rfb_texture_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_positions",
     "rfb_pack_mask", "rfb_cast", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear",
 ]
@@ -80,6 +88,7 @@ def load() -> C.CDLL:
         "rfb_gemm": [C.POINTER(GemmArgs), p],
         "rfb_attention": [C.POINTER(AttnArgs), p],
         "rfb_rmsnorm": [p, ll, p, p, i, ll, i, i, f, p, p],
+        "rfb_rowstat": [p, p, i, p, i, i, i, i, p],
         "rfb_qknorm_rope": [p, ll, i, p, p, ll, i, i, i, f, p, p, i, p],
         "rfb_token_assemble": [p, p, p, p, p, p, i, p, i, i, i, i, p],
         "rfb_texture_prep": [p, p, ll, i, i, i, p],

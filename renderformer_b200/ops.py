@@ -48,7 +48,9 @@ def _need_cuda(*ts):
 
 def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *, M=None, N=None, K=None,
          bias=None, res1=None, res2=None, out_act=None, row_map=None, epi=L.EPI_STORE, out_dtype=None,
-         conv=None, w2=None, b2=None, lda=None, ldw=None, ldo=None, ldres=None, bn=0) -> torch.Tensor:
+         conv=None, w2=None, b2=None, lda=None, ldw=None, ldo=None, ldres=None, bn=0,
+         in_sumsq=None, in_rscale=None, scale_dim=0, norm_dim=0, norm_eps=1e-6, out_rscale=None, out_sumsq=None,
+         out16=None, col_mul=None, aux_row_map=None) -> torch.Tensor:
     """out[M,N] = A[M,K] @ W[N,K]^T with fused epilogue.  `conv=(B,H,W,Cin)` switches A to NHWC 3x3
     implicit GEMM.  Shapes default to the tensors' 2-D shapes."""
     _need_cuda(A, W)
@@ -70,13 +72,27 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
     a.dtype = _DT[A.dtype]
     assert W.dtype == A.dtype, "operand dtypes differ"
     a.epi = epi
-    if out is None and out_act is None:
+    if out is None and out_act is None and out16 is None:
         ncols = N // 2 if epi == L.EPI_SWIGLU else (3 if epi == L.EPI_FINAL else N)
         out = torch.empty((M, ncols), dtype=out_dtype or torch.float32, device=A.device)
     ref = out if out is not None else out_act
     a.out, a.out_act = _p(out), _p(out_act)
-    a.out_dtype = _DT[ref.dtype]
-    a.ldo = (ref.stride(0) if ref.dim() == 2 else ref.shape[-1]) if ldo is None else ldo
+    if ref is not None:
+        a.out_dtype = _DT[ref.dtype]
+        a.ldo = (ref.stride(0) if ref.dim() == 2 else ref.shape[-1]) if ldo is None else ldo
+    else:
+        a.out_dtype, a.ldo = L.F32, _rup8(N)
+    if in_sumsq is not None:  # [rows, parts] partial sums of squares (all parts are summed)
+        a.in_sumsq, a.in_sumsq_ld, a.in_sumsq_parts = in_sumsq.data_ptr(), in_sumsq.stride(0), in_sumsq.shape[1]
+        a.norm_dim, a.norm_eps = norm_dim, norm_eps
+    if in_rscale is not None:
+        a.in_rscale, a.scale_dim = in_rscale.data_ptr(), scale_dim
+    a.out_rscale = _p(out_rscale)
+    if out_sumsq is not None:  # [rows, >= N/128]
+        a.out_sumsq, a.out_sumsq_ld = out_sumsq.data_ptr(), out_sumsq.stride(0)
+    if out16 is not None:
+        a.out16, a.out16_dtype, a.ld16 = out16.data_ptr(), _DT[out16.dtype], out16.stride(0)
+    a.col_mul, a.aux_row_map = _p(col_mul), _p(aux_row_map)
     a.bias = _p(bias)
     if res1 is not None:
         a.res1, a.res_dtype = res1.data_ptr(), _DT[res1.dtype]
@@ -88,11 +104,16 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
     a.bn_override = bn
     tag = f"M={M} N={N} K={K} epi={epi} conv={int(conv is not None)} out={a.out_dtype} res={int(res1 is not None)}"
     L.check(_timed("gemm", 2.0 * M * N * K, lambda: lib.rfb_gemm(C.byref(a), _stream()), tag), "rfb_gemm")
-    return out if out is not None else out_act
+    return out if out is not None else (out_act if out_act is not None else out16)
+
+
+def _rup8(n: int) -> int:
+    return (n + 7) // 8 * 8
 
 
 def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0, vt_bs=0, o_bs=0,
-              mask_bits=None, mask_bs=0, mode=0, group_id=None, group_period=0, scale=None):
+              mask_bits=None, mask_bs=0, mode=0, group_id=None, group_period=0, scale=None,
+              q_sumsq=None, k_sumsq=None, sumsq_ld=1, sumsq_parts=1, norm_dim=0, norm_eps=1e-6):
     _need_cuda(Q, K, Vt, O)
     lib = L.load()
     a = L.AttnArgs()
@@ -104,6 +125,8 @@ def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0,
     a.key_mask_bits, a.mask_batch_stride_words = _p(mask_bits), mask_bs
     a.mode, a.group_id, a.group_period = mode, _p(group_id), group_period
     a.scale = scale if scale is not None else 128 ** -0.5
+    a.q_sumsq, a.k_sumsq = _p(q_sumsq), _p(k_sumsq)
+    a.sumsq_ld, a.sumsq_parts, a.norm_dim, a.norm_eps = sumsq_ld, sumsq_parts, norm_dim, norm_eps
     keys = 128 if mode == 1 else Nk
     L.check(_timed("attention", 4.0 * B * H * Nq * keys * 128, lambda: lib.rfb_attention(C.byref(a), _stream()),
                    f"B={B} H={H} Nq={Nq} Nk={Nk} mode={mode}"), "rfb_attention")
@@ -115,6 +138,15 @@ def rmsnorm(x, w, out, *, rows, d, eps=1e-6, gather=None, ldx=None, ldo=None):
     L.check(_timed("rmsnorm", 0.0, lambda: L.load().rfb_rmsnorm(x.data_ptr(), ldx or d, w.data_ptr(), out.data_ptr(), _DT[out.dtype],
                                  ldo or d, rows, d, eps, _p(gather), _stream())), "rfb_rmsnorm")
     return out
+
+
+def rowstat(x, out16, sumsq, *, rows, d):
+    """sumsq: [rows, parts] partial-sum layout (total in part 0, the rest cleared)."""
+    _need_cuda(x, out16, sumsq)
+    L.check(_timed("rowstat", 0.0, lambda: L.load().rfb_rowstat(
+        x.data_ptr(), out16.data_ptr(), _DT[out16.dtype], sumsq.data_ptr(), sumsq.stride(0), sumsq.shape[1], rows, d,
+        _stream())), "rfb_rowstat")
+    return out16, sumsq
 
 
 def qknorm_rope(x, w, out, *, rows, d, nseg, ldx, ldo, in_period=0, pos=None, freqs=None, eps=1e-6):
