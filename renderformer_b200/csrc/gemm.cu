@@ -219,11 +219,19 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long idx, con
 // Row slot `it` of a lane is tile row it*4 + (lane>>3); the per-row metadata (output row, aux
 // row, 1/rms) lives in the row-owner lane and is fetched with a shuffle where it is needed, so
 // the only per-chunk register arrays are the accumulator and the raw residual bits.
+// Epilogue kinds: the generic one reads every feature flag at run time; the two specialised ones
+// fix the flags of the decoder's hot shapes at compile time, which removes the per-row-slot
+// uniform branches (the epilogue is instruction-latency bound: 2 warps per scheduler).
+constexpr int EK_GENERIC = 0;
+constexpr int EK_RESID = 1;   // out f32 = acc*r + res1 f32, + bf16 copy + partial sums of squares
+constexpr int EK_PROJ16 = 2;  // out16 bf16 = acc*r*col_mul only, + partial sums of squares
+
 struct EpiRes {
   uint4 raw[8];  // fp32 residual: 4 floats; 16-bit residuals: res1 in (x,y), res2 in (z,w)
 };
 
 // issue the residual loads of one 32-column chunk (independent of the accumulator)
+template <int EK>
 __device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane, int orow_mine, int n0, EpiRes& e) {
   const int n = n0 + (lane & 7) * 4;
   const bool col_ok = n < p.n_store;
@@ -233,7 +241,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane
     e.raw[it] = make_uint4(0u, 0u, 0u, 0u);
     if (orow >= 0 && col_ok) {
       const long long idx = (long long)orow * p.ldres + n;
-      if (p.res_dtype == RFB_F32) {
+      if (EK == EK_RESID || p.res_dtype == RFB_F32) {
         e.raw[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.res1) + idx);
       } else {
         const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res1) + idx);
@@ -258,9 +266,25 @@ __device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, flo
 
 // Returns (in the row-owner lane) the sum of squares of the stored values of that lane's row
 // over this chunk when p.out_sumsq is set; 0 otherwise.
+template <int EK>
 __device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, float* stage, int lane, int n0,
                                                           const uint32_t (&v)[32], int orow_mine, int arow_mine,
                                                           float rs_mine, const EpiRes& e) {
+  constexpr bool G = EK == EK_GENERIC;
+  const bool f_out = G ? p.out != nullptr : EK == EK_RESID;
+  const bool f_res = G ? p.res1 != nullptr : EK == EK_RESID;
+  const bool f_res32 = G ? p.res_dtype == RFB_F32 : true;
+  const bool f_res2 = G ? p.res2 != nullptr : false;
+  const bool f_out16 = G ? p.out16 != nullptr : true;
+  const bool f_sumsq = G ? p.out_sumsq != nullptr : true;
+  const bool f_act = G ? p.out_act != nullptr : false;
+  const bool f_bias = G ? p.bias != nullptr : false;
+  const bool f_cs = G ? (p.in_rscale && p.scale_dim == 1) : false;
+  const bool f_cm = G ? p.col_mul != nullptr : EK == EK_PROJ16;
+  const bool f_aux = p.aux_row_map != nullptr;
+  const int out_dtype = G ? p.out_dtype : RFB_F32;
+  const int out16_dtype = G ? p.out16_dtype : RFB_BF16;
+  const int res_dtype = G ? p.res_dtype : RFB_F32;
   const int sw = lane & 7;
 #pragma unroll
   for (int g = 0; g < 8; ++g)
@@ -275,11 +299,10 @@ __device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, 
   float cs[4] = {1.f, 1.f, 1.f, 1.f};
   float cm[4] = {1.f, 1.f, 1.f, 1.f};
   if (col_ok) {
-    if (p.bias) load4(p.bias, RFB_F32, n, bias);
-    if (p.in_rscale && p.scale_dim == 1) load4(p.in_rscale, RFB_F32, n, cs);
-    if (p.col_mul) load4(p.col_mul, RFB_F32, n, cm);
+    if (f_bias) load4(p.bias, RFB_F32, n, bias);
+    if (f_cs) load4(p.in_rscale, RFB_F32, n, cs);
+    if (f_cm) load4(p.col_mul, RFB_F32, n, cm);
   }
-  const bool has_res = p.res1 != nullptr;
   float mysq = 0.f;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -287,25 +310,26 @@ __device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, 
     const int orow = __shfl_sync(0xffffffffu, orow_mine, rr);
     const float rs = __shfl_sync(0xffffffffu, rs_mine, rr);
     const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-    float x[4] = {a.x * rs * cs[0] + bias[0], a.y * rs * cs[1] + bias[1], a.z * rs * cs[2] + bias[2],
-                  a.w * rs * cs[3] + bias[3]};
-    if (has_res) {
-      if (p.res_dtype == RFB_F32) {
+    float x[4] = {a.x * rs, a.y * rs, a.z * rs, a.w * rs};
+    if (f_cs) x[0] *= cs[0], x[1] *= cs[1], x[2] *= cs[2], x[3] *= cs[3];
+    if (f_bias) x[0] += bias[0], x[1] += bias[1], x[2] += bias[2], x[3] += bias[3];
+    if (f_res) {
+      if (f_res32) {
         x[0] += __uint_as_float(e.raw[it].x), x[1] += __uint_as_float(e.raw[it].y);
         x[2] += __uint_as_float(e.raw[it].z), x[3] += __uint_as_float(e.raw[it].w);
       } else {
         float r0, r1, r2, r3;
-        unpack16x2(e.raw[it].x, p.res_dtype, r0, r1), unpack16x2(e.raw[it].y, p.res_dtype, r2, r3);
+        unpack16x2(e.raw[it].x, res_dtype, r0, r1), unpack16x2(e.raw[it].y, res_dtype, r2, r3);
         x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
-        if (p.res2) {
-          unpack16x2(e.raw[it].z, p.res_dtype, r0, r1), unpack16x2(e.raw[it].w, p.res_dtype, r2, r3);
+        if (f_res2) {
+          unpack16x2(e.raw[it].z, res_dtype, r0, r1), unpack16x2(e.raw[it].w, res_dtype, r2, r3);
           x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
         }
       }
     }
     const bool ok = orow >= 0 && col_ok;
-    if (ok && p.out) store4(p.out, p.out_dtype, (long long)orow * p.ldo + n, x);
-    if (p.out_sumsq) {  // warp-uniform
+    if (f_out && ok) store4(p.out, out_dtype, (long long)orow * p.ldo + n, x);
+    if (f_sumsq) {  // warp-uniform
       float s = ok ? x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] : 0.f;
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -313,23 +337,113 @@ __device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, 
       const float t = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);  // row it*4 + (lane&3) -> its owner lane
       if ((lane >> 2) == it) mysq += t;
     }
-    if (p.out16) {  // warp-uniform
-      const int arow = __shfl_sync(0xffffffffu, arow_mine, rr);
+    if (f_out16) {  // warp-uniform
+      int arow = orow;
+      if (f_aux) arow = __shfl_sync(0xffffffffu, arow_mine, rr);
       if (ok) {
-        const float y[4] = {x[0] * cm[0], x[1] * cm[1], x[2] * cm[2], x[3] * cm[3]};
-        store4(p.out16, p.out16_dtype, (long long)arow * p.ld16 + n, y);
+        float y[4] = {x[0], x[1], x[2], x[3]};
+        if (f_cm) y[0] *= cm[0], y[1] *= cm[1], y[2] *= cm[2], y[3] *= cm[3];
+        store4(p.out16, out16_dtype, (long long)arow * p.ld16 + n, y);
       }
     }
-    if (ok && p.out_act) {
+    if (f_act && ok) {
       x[0] = silu_f(x[0]), x[1] = silu_f(x[1]), x[2] = silu_f(x[2]), x[3] = silu_f(x[3]);
-      store4(p.out_act, p.out_dtype, (long long)orow * p.ldo + n, x);
+      store4(p.out_act, out_dtype, (long long)orow * p.ldo + n, x);
     }
   }
   __syncwarp();
   return mysq;
 }
 
-template <int BN>
+// ---------------------------------------------------------------------------------------------
+// Specialised epilogue of one warp's half tile (4 chunks of 32 columns, BN == 256, N % 256 == 0)
+// for EK_RESID / EK_PROJ16.  Everything that is constant over the tile's chunks (output rows,
+// 1/rms, smem addresses) lives in registers, the chunk loop is fully unrolled so the residual
+// prefetch ping-pongs between two register sets without copies, and the sums of squares are
+// reduced across lanes once per tile instead of once per chunk.
+// ---------------------------------------------------------------------------------------------
+template <int EK>
+__device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, float* stage, int lane, uint32_t taddr,
+                                                        int n_begin, int orow_mine, int arow_mine, float rs_mine,
+                                                        uint64_t* tfull_bar, uint32_t parity) {
+  constexpr bool RES = EK == EK_RESID;
+  const int c4 = lane & 7;
+  const int g4 = lane >> 3;
+  int orow[8], arow[8];
+  float rs[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    orow[it] = __shfl_sync(0xffffffffu, orow_mine, it * 4 + g4);
+    arow[it] = __shfl_sync(0xffffffffu, arow_mine, it * 4 + g4);
+    rs[it] = __shfl_sync(0xffffffffu, rs_mine, it * 4 + g4);
+  }
+  float sqp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* res = static_cast<const float*>(p.res1);
+  float* out = static_cast<float*>(p.out);
+  uint16_t* out16 = static_cast<uint16_t*>(p.out16);
+  uint4 ra[8], rb[8];
+  auto prefetch = [&](uint4(&r)[8], int n) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (orow[it] >= 0) r[it] = *reinterpret_cast<const uint4*>(res + (long long)orow[it] * p.ldres + n);
+  };
+  if (RES) prefetch(ra, n_begin + c4 * 4);
+  mbar_wait(tfull_bar, parity);
+  tc_fence_after();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+    const int n = n_begin + c * 32 + c4 * 4;
+    if (RES && c + 1 < 4) {
+      if (c & 1) prefetch(ra, n + 32);
+      else prefetch(rb, n + 32);
+    }
+    float cm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (!RES) load4(p.col_mul, RFB_F32, n, cm);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ c4) << 2)) =
+          make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                      __uint_as_float(v[g * 4 + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + g4;
+      const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+      float x[4] = {a.x * rs[it], a.y * rs[it], a.z * rs[it], a.w * rs[it]};
+      if (RES) {
+        const uint4& r = (c & 1) ? rb[it] : ra[it];
+        x[0] += __uint_as_float(r.x), x[1] += __uint_as_float(r.y);
+        x[2] += __uint_as_float(r.z), x[3] += __uint_as_float(r.w);
+      }
+      if (orow[it] >= 0) {
+        if (RES) *reinterpret_cast<float4*>(out + (long long)orow[it] * p.ldo + n) = make_float4(x[0], x[1], x[2], x[3]);
+        sqp[it] += x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+        uint2 u;
+        u.x = pack_bf16(x[0] * cm[0], x[1] * cm[1]), u.y = pack_bf16(x[2] * cm[2], x[3] * cm[3]);
+        *reinterpret_cast<uint2*>(out16 + (long long)arow[it] * p.ld16 + n) = u;
+      }
+    }
+    __syncwarp();
+  }
+  // one 128-column part per warp: reduce the 8 column lanes of every row slot, owner lane writes
+  float mine = 0.f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float t = sqp[it];
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t = __shfl_sync(0xffffffffu, t, (lane & 3) * 8);
+    if ((lane >> 2) == it) mine = t;
+  }
+  if (orow_mine >= 0) p.out_sumsq[(long long)arow_mine * p.out_sumsq_ld + (n_begin >> 7)] = mine;
+}
+
+
+template <int BN, int EK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmKParams p) {
@@ -485,41 +599,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           rs = p.in_rscale[mt * kBM + r];
         }
       }
-      const bool coalesced = (p.epi == RFB_EPI_STORE) && !p.direct_store;
       float* my_stage = epi_stage + (warp - 2) * 32 * 32;
       // the two warps of a TMEM lane quarter take the two contiguous halves of the tile's columns
       constexpr int NCH = BN / 32;
       constexpr int HALF = (NCH + 1) / 2;
       const int c_begin = ((warp - 2) >> 2) * HALF;
       const int c_end = (c_begin + HALF < NCH) ? c_begin + HALF : NCH;
-      const bool has_res = coalesced && p.res1 != nullptr;
-      EpiRes cur, nxt;
-      // the first chunk's residual does not depend on the accumulator: fetch it while the
-      // main loop of this tile is still running
-      if (has_res && c_begin < c_end && n0 + c_begin * 32 < p.n_store)
-        epilogue_prefetch(p, lane, orow_mine, n0 + c_begin * 32, cur);
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      float sq = 0.f;
+      if constexpr (EK != EK_GENERIC) {
+        static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
+        epilogue_half_tile_fast<EK>(p, my_stage, lane,
+                                    tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
+                                    n0 + c_begin * 32, orow_mine, arow_mine, rs, &tfull[as], aph);
+      } else {
+        const bool coalesced = (p.epi == RFB_EPI_STORE) && !p.direct_store;
+        const bool has_res = coalesced && p.res1 != nullptr;
+        EpiRes cur, nxt;
+        // the first chunk's residual does not depend on the accumulator: fetch it while the
+        // main loop of this tile is still running
+        if (has_res && c_begin < c_end && n0 + c_begin * 32 < p.n_store)
+          epilogue_prefetch<EK>(p, lane, orow_mine, n0 + c_begin * 32, cur);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        float sq = 0.f;
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-        if (coalesced) {
-          if (has_res && c + 1 < c_end && n0 + (c + 1) * 32 < p.n_store)
-            epilogue_prefetch(p, lane, orow_mine, n0 + (c + 1) * 32, nxt);
-          tmem_wait_ld();
-          sq += epilogue_store_coalesced(p, my_stage, lane, n0 + c * 32, v, orow_mine, arow_mine, rs, cur);
-          cur = nxt;
-        } else {
-          tmem_wait_ld();
-          if (valid) epilogue_chunk(p, orow, n0 + c * 32, v, rs);
+        for (int c = c_begin; c < c_end; ++c) {
+          if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
+          if (coalesced) {
+            if (has_res && c + 1 < c_end && n0 + (c + 1) * 32 < p.n_store)
+              epilogue_prefetch<EK>(p, lane, orow_mine, n0 + (c + 1) * 32, nxt);
+            tmem_wait_ld();
+            sq += epilogue_store_coalesced<EK>(p, my_stage, lane, n0 + c * 32, v, orow_mine, arow_mine, rs, cur);
+            cur = nxt;
+          } else {
+            tmem_wait_ld();
+            if (valid) epilogue_chunk(p, orow, n0 + c * 32, v, rs);
+          }
         }
+        // BN == 256 whenever out_sumsq is set: this warp's columns are exactly one 128-column part
+        if (coalesced && p.out_sumsq && valid && n0 + c_begin * 32 < p.n_store)
+          p.out_sumsq[static_cast<long long>(arow_mine) * p.out_sumsq_ld + ((n0 + c_begin * 32) >> 7)] = sq;
       }
-      // BN == 256 whenever out_sumsq is set: this warp's columns are exactly one 128-column part
-      if (coalesced && p.out_sumsq && valid && n0 + c_begin * 32 < p.n_store)
-        p.out_sumsq[static_cast<long long>(arow_mine) * p.out_sumsq_ld + ((n0 + c_begin * 32) >> 7)] = sq;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -534,18 +655,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-template <int BN>
+template <int BN, int EK = EK_GENERIC>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                        int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmemBytes) != cudaSuccess)
       return RFB_ERR_LAUNCH;
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, EK><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   g_launch_count++;
   return check_launch("gemm_tc_kernel");
 }
@@ -671,6 +792,12 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
   int grid = (int)(total < cap ? total : cap);
 
+  if (bn == 256 && a->N % 256 == 0 && a->epi == RFB_EPI_STORE && !p.direct_store && a->out16 && a->out16_dtype == RFB_BF16 &&
+      a->out_sumsq && !a->bias && !a->res2 && !a->out_act && !(a->in_rscale && a->scale_dim == 1)) {
+    if (a->out && a->out_dtype == RFB_F32 && a->res1 && a->res_dtype == RFB_F32 && !a->col_mul)
+      return launch_gemm<256, EK_RESID>(tmA, tmB, p, grid, stream);
+    if (!a->out && !a->res1 && a->col_mul) return launch_gemm<256, EK_PROJ16>(tmA, tmB, p, grid, stream);
+  }
   switch (bn) {
     case 32: return launch_gemm<32>(tmA, tmB, p, grid, stream);
     case 64: return launch_gemm<64>(tmA, tmB, p, grid, stream);

@@ -1,5 +1,6 @@
 // Standalone GPU self-test + micro-benchmark of rfb_gemm (no torch).
 // Checks every epilogue / A-operand mode against a naive CUDA-core reference kernel.
+#include <stdlib.h>
 #include <string.h>
 
 #include "selftest_common.h"
@@ -190,8 +191,10 @@ static void run_case(const Case& c) {
 
 // fused-RMSNorm plumbing: in_sumsq partial sums / in_rscale (row or column), out_rscale,
 // out_sumsq partial sums, out16 (+col_mul, aux map)
+// kind: 0 = everything at once (generic epilogue), 1 = residual-stream shape (no col_mul -> EK_RESID when
+// N % 256 == 0), 2 = 16-bit projection shape (no fp32 out, no residual -> EK_PROJ16)
 static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool swiglu, bool use_map, bool with_res,
-                      bool rowmap = false) {
+                      bool rowmap = false, int kind = 0) {
   std::vector<uint16_t> hA = rand16((size_t)M * K, 5, 1.0f, RFB_BF16), hW = rand16((size_t)N * K, 6, 0.05f, RFB_BF16);
   DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K);
   dA.up(hA), dW.up(hW);
@@ -244,10 +247,12 @@ static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool
   if (swiglu) {
     a.epi = RFB_EPI_SWIGLU, a.out = doutb.p, a.out_dtype = RFB_BF16, a.ldo = ocols;
   } else {
-    a.epi = RFB_EPI_STORE, a.out = dout.p, a.out_dtype = RFB_F32, a.ldo = N;
+    a.epi = RFB_EPI_STORE, a.out = kind == 2 ? nullptr : dout.p, a.out_dtype = RFB_F32, a.ldo = N;
     if (with_res) a.res1 = dres.p, a.res_dtype = RFB_F32, a.ldres = N;
     if (want_sq) a.out_sumsq = dosq.p, a.out_sumsq_ld = nparts;
-    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = dcm.p;
+    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = kind == 1 ? nullptr : dcm.p;
+    if (kind == 1)
+      for (auto& c : hcm) c = 1.0f;
     a.aux_row_map = use_map ? dmap.p : nullptr;
     a.row_map = rowmap ? drmap.p : nullptr;
   }
@@ -283,7 +288,7 @@ static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool
     }
   }
   std::string nm(name);
-  report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, N);
+  if (kind != 2) report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, N);
   report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * N, RFB_BF16), exp16, 2e-2, 1.2e-2, N);
   if (want_sq) report((nm + " [sumsq]").c_str(), dosq.down(), expsq, 1e-2, 2e-3, nparts);
   if (scale_dim == 0) report((nm + " [rscale]").c_str(), drs.down(), hscale, 1e-5, 1e-4, 1);
@@ -295,8 +300,11 @@ static void bench_fused(const char* name, int M, int N, int K, bool res, bool su
   DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K), d16((size_t)M * N);
   CK(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2));
   CK(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2));
-  DevBuf<float> dx((size_t)M * N), dsq((size_t)M * (N / 128)), dinsq((size_t)M * 8), dcm(N);
-  dx.zero(), dinsq.zero(), dcm.zero();
+  const int pad = getenv("RFB_PAD") ? atoi(getenv("RFB_PAD")) : 0;   // experiment: padded row pitch
+  const bool sep = getenv("RFB_SEP") != nullptr;                      // experiment: out != res
+  const long long ldx = N + pad;
+  DevBuf<float> dx((size_t)M * ldx), dx2((size_t)M * ldx), dsq((size_t)M * (N / 128)), dinsq((size_t)M * 8), dcm(N);
+  dx.zero(), dx2.zero(), dinsq.zero(), dcm.zero();
   std::vector<int> hmap(M);
   for (int m = 0; m < M; ++m) hmap[m] = (int)(((long long)m * 8191 + 17) % M);
   DevBuf<int> dmap(M);
@@ -304,11 +312,11 @@ static void bench_fused(const char* name, int M, int N, int K, bool res, bool su
   rfb_gemm_args a;
   memset(&a, 0, sizeof(a));
   a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = K, a.W = dW.p, a.ldw = K, a.dtype = RFB_BF16;
-  a.epi = RFB_EPI_STORE, a.out_dtype = RFB_F32, a.ldo = N;
-  if (f32out) a.out = dx.p;
-  if (res) a.res1 = dx.p, a.res_dtype = RFB_F32, a.ldres = N;
+  a.epi = RFB_EPI_STORE, a.out_dtype = RFB_F32, a.ldo = ldx;
+  if (f32out) a.out = sep ? dx2.p : dx.p;
+  if (res) a.res1 = dx.p, a.res_dtype = RFB_F32, a.ldres = ldx;
   if (sumsq) a.out_sumsq = dsq.p, a.out_sumsq_ld = N / 128;
-  if (o16) a.out16 = d16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = dcm.p;
+  if (o16) a.out16 = d16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = res ? nullptr : dcm.p;
   if (in_sq) a.in_sumsq = dinsq.p, a.in_sumsq_ld = 8, a.in_sumsq_parts = 8, a.norm_dim = 1024, a.norm_eps = 1e-6f;
   if (maps) a.row_map = dmap.p;
   for (int i = 0; i < 3; ++i) {
@@ -375,6 +383,11 @@ int main(int argc, char** argv) {
           argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 0, argc > 10 ? atoi(argv[10]) : 1);
     return 0;
   }
+  if (argc >= 11 && !strcmp(argv[1], "fone")) {  // fone M N K res sumsq o16 insq maps f32out
+    bench_fused("fone", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]),
+                atoi(argv[8]), atoi(argv[9]), atoi(argv[10]));
+    return 0;
+  }
   const bool do_bench = argc > 1 && !strcmp(argv[1], "bench");
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("rfb version %d\n", rfb_version());
@@ -407,6 +420,9 @@ int main(int argc, char** argv) {
       run_fused("fused rowscale auxmap 517x512x256", 517, 512, 256, 0, false, true, false);
       run_fused("fused rowscale rowmap+res 1031x640x256", 1031, 640, 256, 0, false, false, true, true);
       run_fused("fused colscale 1024x1096x512", 1024, 1096, 512, 1, false, false, false);
+      run_fused("EK_RESID 1031x1024x512 res", 1031, 1024, 512, 0, false, false, true, false, 1);
+      run_fused("EK_RESID 1031x512x256 res rowmap auxmap", 1031, 512, 256, 0, false, true, true, true, 1);
+      run_fused("EK_PROJ16 1031x2048x256", 1031, 2048, 256, 0, false, false, false, false, 2);
       run_fused("fused swiglu rowscale 777x2048x512", 777, 2048, 512, 0, true, false, false);
     }
     printf("selftest_gemm: %d failure(s)\n", g_fail);
