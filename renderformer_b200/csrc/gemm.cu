@@ -226,35 +226,6 @@ constexpr int EK_GENERIC = 0;
 constexpr int EK_RESID = 1;   // out f32 = acc*r + res1 f32, + bf16 copy + partial sums of squares
 constexpr int EK_PROJ16 = 2;  // out16 bf16 = acc*r*col_mul only, + partial sums of squares
 
-struct EpiRes {
-  uint4 raw[8];  // fp32 residual: 4 floats; 16-bit residuals: res1 in (x,y), res2 in (z,w)
-};
-
-// issue the residual loads of one 32-column chunk (independent of the accumulator)
-template <int EK>
-__device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int lane, int orow_mine, int n0, EpiRes& e) {
-  const int n = n0 + (lane & 7) * 4;
-  const bool col_ok = n < p.n_store;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int orow = __shfl_sync(0xffffffffu, orow_mine, it * 4 + (lane >> 3));
-    e.raw[it] = make_uint4(0u, 0u, 0u, 0u);
-    if (orow >= 0 && col_ok) {
-      const long long idx = (long long)orow * p.ldres + n;
-      if (EK == EK_RESID || p.res_dtype == RFB_F32) {
-        e.raw[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.res1) + idx);
-      } else {
-        const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res1) + idx);
-        e.raw[it].x = a.x, e.raw[it].y = a.y;
-        if (p.res2) {
-          const uint2 b = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res2) + idx);
-          e.raw[it].z = b.x, e.raw[it].w = b.y;
-        }
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, float& hi) {
   if (dtype == RFB_BF16) {
     lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
@@ -264,95 +235,176 @@ __device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, flo
   }
 }
 
-// Returns (in the row-owner lane) the sum of squares of the stored values of that lane's row
-// over this chunk when p.out_sumsq is set; 0 otherwise.
-template <int EK>
-__device__ __forceinline__ float epilogue_store_coalesced(const GemmKParams& p, float* stage, int lane, int n0,
-                                                          const uint32_t (&v)[32], int orow_mine, int arow_mine,
-                                                          float rs_mine, const EpiRes& e) {
-  constexpr bool G = EK == EK_GENERIC;
-  const bool f_out = G ? p.out != nullptr : EK == EK_RESID;
-  const bool f_res = G ? p.res1 != nullptr : EK == EK_RESID;
-  const bool f_res32 = G ? p.res_dtype == RFB_F32 : true;
-  const bool f_res2 = G ? p.res2 != nullptr : false;
-  const bool f_out16 = G ? p.out16 != nullptr : true;
-  const bool f_sumsq = G ? p.out_sumsq != nullptr : true;
-  const bool f_act = G ? p.out_act != nullptr : false;
-  const bool f_bias = G ? p.bias != nullptr : false;
-  const bool f_cs = G ? (p.in_rscale && p.scale_dim == 1) : false;
-  const bool f_cm = G ? p.col_mul != nullptr : EK == EK_PROJ16;
-  const bool f_aux = p.aux_row_map != nullptr;
-  const int out_dtype = G ? p.out_dtype : RFB_F32;
-  const int out16_dtype = G ? p.out16_dtype : RFB_BF16;
-  const int res_dtype = G ? p.res_dtype : RFB_F32;
-  const int sw = lane & 7;
-#pragma unroll
-  for (int g = 0; g < 8; ++g)
-    *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ sw) << 2)) =
-        make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
-                    __uint_as_float(v[g * 4 + 3]));
-  __syncwarp();
+// ---------------------------------------------------------------------------------------------
+// Generic RFB_EPI_STORE epilogue of one warp's share [c_begin, c_end) of the tile's 32-column
+// chunks; every feature is a run-time (warp-uniform) flag.  The work of a chunk is split into
+// one straight-line pass over the 8 row slots per feature ("loop fission"), so a flag costs one
+// uniform branch per chunk instead of one per row slot and each pass schedules as a block.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p, float* stage, int lane,
+                                                           uint32_t taddr0, int n0, int c_begin, int c_end,
+                                                           int orow_mine, int arow_mine, float rs_mine,
+                                                           uint64_t* tfull_bar, uint32_t parity) {
   const int c4 = lane & 7;
-  const int n = n0 + c4 * 4;
-  const bool col_ok = n < p.n_store;
-  float bias[4] = {0.f, 0.f, 0.f, 0.f};
-  float cs[4] = {1.f, 1.f, 1.f, 1.f};
-  float cm[4] = {1.f, 1.f, 1.f, 1.f};
-  if (col_ok) {
-    if (f_bias) load4(p.bias, RFB_F32, n, bias);
-    if (f_cs) load4(p.in_rscale, RFB_F32, n, cs);
-    if (f_cm) load4(p.col_mul, RFB_F32, n, cm);
-  }
-  float mysq = 0.f;
+  const int g4 = lane >> 3;
+  int orow[8];
+  float rs[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    const int orow = __shfl_sync(0xffffffffu, orow_mine, rr);
-    const float rs = __shfl_sync(0xffffffffu, rs_mine, rr);
-    const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-    float x[4] = {a.x * rs, a.y * rs, a.z * rs, a.w * rs};
-    if (f_cs) x[0] *= cs[0], x[1] *= cs[1], x[2] *= cs[2], x[3] *= cs[3];
-    if (f_bias) x[0] += bias[0], x[1] += bias[1], x[2] += bias[2], x[3] += bias[3];
-    if (f_res) {
+    orow[it] = __shfl_sync(0xffffffffu, orow_mine, it * 4 + g4);
+    rs[it] = __shfl_sync(0xffffffffu, rs_mine, it * 4 + g4);
+  }
+  const bool f_out = p.out != nullptr, f_res = p.res1 != nullptr, f_res32 = p.res_dtype == RFB_F32;
+  const bool f_res2 = p.res2 != nullptr, f_out16 = p.out16 != nullptr, f_sumsq = p.out_sumsq != nullptr;
+  const bool f_act = p.out_act != nullptr, f_bias = p.bias != nullptr, f_cm = p.col_mul != nullptr;
+  const bool f_cs = p.in_rscale != nullptr && p.scale_dim == 1;
+  float sqp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4 cur[8], nxt[8];  // raw residual bits; 16-bit residuals: res1 in (x,y), res2 in (z,w)
+  auto prefetch = [&](uint4(&r)[8], int n) {
+    if (n >= p.n_store) return;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if (orow[it] < 0) continue;
+      const long long idx = (long long)orow[it] * p.ldres + n;
       if (f_res32) {
-        x[0] += __uint_as_float(e.raw[it].x), x[1] += __uint_as_float(e.raw[it].y);
-        x[2] += __uint_as_float(e.raw[it].z), x[3] += __uint_as_float(e.raw[it].w);
+        r[it] = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.res1) + idx);
       } else {
-        float r0, r1, r2, r3;
-        unpack16x2(e.raw[it].x, res_dtype, r0, r1), unpack16x2(e.raw[it].y, res_dtype, r2, r3);
-        x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
+        const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res1) + idx);
+        r[it].x = a.x, r[it].y = a.y;
         if (f_res2) {
-          unpack16x2(e.raw[it].z, res_dtype, r0, r1), unpack16x2(e.raw[it].w, res_dtype, r2, r3);
-          x[0] += r0, x[1] += r1, x[2] += r2, x[3] += r3;
+          const uint2 b = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.res2) + idx);
+          r[it].z = b.x, r[it].w = b.y;
         }
       }
     }
-    const bool ok = orow >= 0 && col_ok;
-    if (f_out && ok) store4(p.out, out_dtype, (long long)orow * p.ldo + n, x);
-    if (f_sumsq) {  // warp-uniform
-      float s = ok ? x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] : 0.f;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      const float t = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);  // row it*4 + (lane&3) -> its owner lane
-      if ((lane >> 2) == it) mysq += t;
+  };
+  // the first chunk's residual does not depend on the accumulator: fetch it while the main loop
+  // of this tile is still running
+  if (f_res && c_begin < c_end) prefetch(cur, n0 + c_begin * 32 + c4 * 4);
+  mbar_wait(tfull_bar, parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(taddr0 + c * 32, v);
+    const int n = n0 + c * 32 + c4 * 4;
+    const bool col_ok = n < p.n_store;
+    if (f_res && c + 1 < c_end) prefetch(nxt, n + 32);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ c4) << 2)) =
+          make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                      __uint_as_float(v[g * 4 + 3]));
+    __syncwarp();
+    float x[8][4];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + g4;
+      const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+      x[it][0] = a.x * rs[it], x[it][1] = a.y * rs[it], x[it][2] = a.z * rs[it], x[it][3] = a.w * rs[it];
     }
-    if (f_out16) {  // warp-uniform
-      int arow = orow;
-      if (f_aux) arow = __shfl_sync(0xffffffffu, arow_mine, rr);
-      if (ok) {
-        float y[4] = {x[0], x[1], x[2], x[3]};
-        if (f_cm) y[0] *= cm[0], y[1] *= cm[1], y[2] *= cm[2], y[3] *= cm[3];
-        store4(p.out16, out16_dtype, (long long)arow * p.ld16 + n, y);
+    __syncwarp();
+    if (f_cs || f_bias) {
+      float cs[4] = {1.f, 1.f, 1.f, 1.f}, bias[4] = {0.f, 0.f, 0.f, 0.f};
+      if (col_ok && f_cs) load4(p.in_rscale, RFB_F32, n, cs);
+      if (col_ok && f_bias) load4(p.bias, RFB_F32, n, bias);
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[it][j] = fmaf(x[it][j], cs[j], bias[j]);
+    }
+    if (f_res) {
+      if (f_res32) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          x[it][0] += __uint_as_float(cur[it].x), x[it][1] += __uint_as_float(cur[it].y);
+          x[it][2] += __uint_as_float(cur[it].z), x[it][3] += __uint_as_float(cur[it].w);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float r0, r1, r2, r3;
+          unpack16x2(cur[it].x, p.res_dtype, r0, r1), unpack16x2(cur[it].y, p.res_dtype, r2, r3);
+          x[it][0] += r0, x[it][1] += r1, x[it][2] += r2, x[it][3] += r3;
+        }
+        if (f_res2) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float r0, r1, r2, r3;
+            unpack16x2(cur[it].z, p.res_dtype, r0, r1), unpack16x2(cur[it].w, p.res_dtype, r2, r3);
+            x[it][0] += r0, x[it][1] += r1, x[it][2] += r2, x[it][3] += r3;
+          }
+        }
       }
     }
-    if (f_act && ok) {
-      x[0] = silu_f(x[0]), x[1] = silu_f(x[1]), x[2] = silu_f(x[2]), x[3] = silu_f(x[3]);
-      store4(p.out_act, out_dtype, (long long)orow * p.ldo + n, x);
+    if (f_out) {
+      if (p.out_dtype == RFB_F32) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (orow[it] >= 0 && col_ok) store4(p.out, RFB_F32, (long long)orow[it] * p.ldo + n, x[it]);
+      } else if (p.out_dtype == RFB_BF16) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (orow[it] >= 0 && col_ok) store4(p.out, RFB_BF16, (long long)orow[it] * p.ldo + n, x[it]);
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (orow[it] >= 0 && col_ok) store4(p.out, RFB_F16, (long long)orow[it] * p.ldo + n, x[it]);
+      }
+    }
+    if (f_sumsq) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (orow[it] >= 0 && col_ok)
+          sqp[it] += x[it][0] * x[it][0] + x[it][1] * x[it][1] + x[it][2] * x[it][2] + x[it][3] * x[it][3];
+    }
+    if (f_out16) {
+      float cm[4] = {1.f, 1.f, 1.f, 1.f};
+      if (col_ok && f_cm) load4(p.col_mul, RFB_F32, n, cm);
+      const bool aux = p.aux_row_map != nullptr;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int arow = orow[it];
+        if (aux) arow = __shfl_sync(0xffffffffu, arow_mine, it * 4 + g4);
+        if (orow[it] >= 0 && col_ok) {
+          const float y[4] = {x[it][0] * cm[0], x[it][1] * cm[1], x[it][2] * cm[2], x[it][3] * cm[3]};
+          store4(p.out16, p.out16_dtype, (long long)arow * p.ld16 + n, y);
+        }
+      }
+    }
+    if (f_act) {
+      const bool bf = p.out_dtype == RFB_BF16;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        float y[4] = {silu_f(x[it][0]), silu_f(x[it][1]), silu_f(x[it][2]), silu_f(x[it][3])};
+        if (orow[it] >= 0 && col_ok) {
+          if (p.out_dtype == RFB_F32) store4(p.out_act, RFB_F32, (long long)orow[it] * p.ldo + n, y);
+          else if (bf) store4(p.out_act, RFB_BF16, (long long)orow[it] * p.ldo + n, y);
+          else store4(p.out_act, RFB_F16, (long long)orow[it] * p.ldo + n, y);
+        }
+      }
+    }
+    if (f_res) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
     }
   }
-  __syncwarp();
-  return mysq;
+  // BN == 256 whenever out_sumsq is set: this warp's columns are exactly one 128-column part
+  if (f_sumsq && n0 + c_begin * 32 < p.n_store) {
+    float mine = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float t = sqp[it];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t = __shfl_sync(0xffffffffu, t, (lane & 3) * 8);
+      if ((lane >> 2) == it) mine = t;
+    }
+    if (orow_mine >= 0) p.out_sumsq[(long long)arow_mine * p.out_sumsq_ld + ((n0 + c_begin * 32) >> 7)] = mine;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -611,35 +663,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                     tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
                                     n0 + c_begin * 32, orow_mine, arow_mine, rs, &tfull[as], aph);
       } else {
-        const bool coalesced = (p.epi == RFB_EPI_STORE) && !p.direct_store;
-        const bool has_res = coalesced && p.res1 != nullptr;
-        EpiRes cur, nxt;
-        // the first chunk's residual does not depend on the accumulator: fetch it while the
-        // main loop of this tile is still running
-        if (has_res && c_begin < c_end && n0 + c_begin * 32 < p.n_store)
-          epilogue_prefetch<EK>(p, lane, orow_mine, n0 + c_begin * 32, cur);
-        mbar_wait(&tfull[as], aph);
-        tc_fence_after();
-        float sq = 0.f;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+        if ((p.epi == RFB_EPI_STORE) && !p.direct_store) {
+          epilogue_generic_coalesced(p, my_stage, lane, taddr0, n0, c_begin, c_end, orow_mine, arow_mine, rs,
+                                     &tfull[as], aph);
+        } else {
+          mbar_wait(&tfull[as], aph);
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-          if (coalesced) {
-            if (has_res && c + 1 < c_end && n0 + (c + 1) * 32 < p.n_store)
-              epilogue_prefetch<EK>(p, lane, orow_mine, n0 + (c + 1) * 32, nxt);
-            tmem_wait_ld();
-            sq += epilogue_store_coalesced<EK>(p, my_stage, lane, n0 + c * 32, v, orow_mine, arow_mine, rs, cur);
-            cur = nxt;
-          } else {
+          for (int c = c_begin; c < c_end; ++c) {
+            if (n0 + c * 32 >= p.n_store) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr0 + c * 32, v);
             tmem_wait_ld();
             if (valid) epilogue_chunk(p, orow, n0 + c * 32, v, rs);
           }
         }
-        // BN == 256 whenever out_sumsq is set: this warp's columns are exactly one 128-column part
-        if (coalesced && p.out_sumsq && valid && n0 + c_begin * 32 < p.n_store)
-          p.out_sumsq[static_cast<long long>(arow_mine) * p.out_sumsq_ld + ((n0 + c_begin * 32) >> 7)] = sq;
       }
       tc_fence_before();
       __syncwarp();
