@@ -14,7 +14,6 @@ fp16 operands in the token encoders and the DPT head, fp32 accumulation / softma
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -42,11 +41,21 @@ class SceneState:
     tri: torch.Tensor        # fp32 [B, N, 9]
     mask_u8: torch.Tensor    # uint8 [B, N]
     mask_bits: torch.Tensor  # int32 [B, words]
-    k_pre: List[torch.Tensor]  # per decoder layer fp32 [B, Ntp, dv]  (pre-norm, pre-RoPE)
-    v_t: List[torch.Tensor]    # per decoder layer bf16 [B, dv, Ntp]  (transposed)
+    k_all: torch.Tensor      # fp32 [B, Ntp, L*dv]: hoisted decoder K of every layer (pre-QK-norm, pre-RoPE)
+    v_all: torch.Tensor      # bf16 [B, L*dv, Ntp]: hoisted decoder V of every layer, transposed
+
+    dv: int = 0              # decoder width (columns of one layer inside k_all / rows inside v_all)
+
+    def k_pre(self, layer: int, b: int) -> torch.Tensor:
+        """fp32 [Ntp, dv] view (row stride L*dv)."""
+        return self.k_all[b, :, layer * self.dv:(layer + 1) * self.dv]
+
+    def v_t(self, layer: int, b: int) -> torch.Tensor:
+        """bf16 [dv, Ntp] contiguous view."""
+        return self.v_all[b, layer * self.dv:(layer + 1) * self.dv]
 
     def tensors(self):
-        return [self.seq, self.tri, self.mask_u8, self.mask_bits] + self.k_pre + self.v_t
+        return [self.seq, self.tri, self.mask_u8, self.mask_bits, self.k_all, self.v_all]
 
 
 def swin_window_maps(Hp: int, Wp: int, shift: int, ws: int = 8):
@@ -77,9 +86,10 @@ class Engine:
         if self.device.type != "cuda":
             raise L.RfbError("renderformer_b200.Engine needs a CUDA device (there is no CPU fallback)")
         L.load()
-        # fused RMSNorm (norm weights folded into the next GEMM, 1/rms applied in its epilogue from
-        # sums of squares maintained by the residual GEMMs); RFB_UNFUSED=1 keeps the explicit kernels
-        self.fused = os.environ.get("RFB_UNFUSED", "0") != "1"
+        # RMSNorm is fused into the GEMMs (norm weights folded into the next projection, 1/rms applied
+        # in its epilogue from partial sums of squares left by the residual GEMMs) in the scene stage
+        # and in the swin decoder; the full-attention decoder (V1-Base) keeps explicit norm kernels.
+        self.fused_dec = bool(cfg.view_transformer_use_swin_attn)
         self.w: Dict[str, torch.Tensor] = {}
         self._maps: Dict[tuple, tuple] = {}
         self._prepare(state_dict)
@@ -104,14 +114,10 @@ class Engine:
             w = g(k)
             return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
-        fused = self.fused
-
-        def fold(wt, norm_key, on=fused):  # RMSNorm(x) W^T = r * x (W . w)^T : fold the norm weight along K
+        def fold(wt, norm_key, on=True):  # RMSNorm(x) W^T = r * x (W . w)^T : fold the norm weight along K
             return wt * g(norm_key)[None, :] if on else wt
 
-        # the fused decoder exists for the swin architecture only; the hoisted K/V projections are
-        # part of the (always fused) scene stage
-        fused_dec = self.fused_dec = fused and cfg.view_transformer_use_swin_attn
+        fused_dec = self.fused_dec
 
         d = cfg.latent_dim
         put("tri_token", g("tri_token").reshape(-1))
@@ -130,7 +136,6 @@ class Engine:
             put(o + "wqk", w_in[: 2 * d], bf), put(o + "wv", w_in[2 * d:], bf)
             put(o + "wo", g(p + "multihead_attn.out_proj.weight"), bf)
             put(o + "qkn", torch.cat([g(p + "multihead_attn.q_norm.weight"), g(p + "multihead_attn.k_norm.weight")]))
-            put(o + "n1", g(p + "query_norm.weight")), put(o + "n2", g(p + "ffn_norm.weight"))
             put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight"), bf)
             put(o + "w2", g(p + "ffn.w2.weight"), bf)
 
@@ -147,7 +152,7 @@ class Engine:
             put(o + "wv", fold(g(p + "multihead_attn.v_proj.weight"), p + "kv_norm.weight"), bf)
             put(o + "wout", g(p + "multihead_attn.out_proj.weight"), bf)
             put(o + "qn", g(p + "multihead_attn.q_norm.weight")), put(o + "kn", g(p + "multihead_attn.k_norm.weight"))
-            put(o + "n_q", g(p + "query_norm.weight")), put(o + "n_kv", g(p + "kv_norm.weight"))
+            put(o + "n_q", g(p + "query_norm.weight"))
             w_in = fold(g(p + "self_attn.in_proj.weight"), p + "self_attn_norm.weight", fused_dec)
             put(o + "s.wqk", w_in[: 2 * dv], bf), put(o + "s.wv", w_in[2 * dv:], bf)
             put(o + "s.wo", g(p + "self_attn.out_proj.weight"), bf)
@@ -155,6 +160,10 @@ class Engine:
             put(o + "n_s", g(p + "self_attn_norm.weight")), put(o + "n_f", g(p + "ffn_norm.weight"))
             put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight", fused_dec), bf)
             put(o + "w2", g(p + "ffn.w2.weight"), bf)
+
+        Lv = cfg.view_transformer_n_layers
+        put("dec.wk_all", torch.cat([self.w.pop(f"dec{i}.wk") for i in range(Lv)], dim=0))
+        put("dec.wv_all", torch.cat([self.w.pop(f"dec{i}.wv") for i in range(Lv)], dim=0))
 
         h = v + "out_dpt."
         for i in range(4):
@@ -218,39 +227,7 @@ class Engine:
         words = 4 * ((Ntp + 127) // 128)
         bits = ops.pack_mask(mask_u8, self._e((B, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=B)
 
-        if self.fused:
-            return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8)
-
-        # encoder  (layers/attention.py:579-590)
-        rows = B * Ntp
-        for i in range(cfg.num_layers):
-            o = f"enc{i}."
-            h = ops.rmsnorm(x, w[o + "n1"], self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
-            qk = ops.gemm(h, w[o + "wqk"], out_dtype=torch.float32)
-            vt = self._e((B, d, Ntp), torch.bfloat16)
-            for b in range(B):
-                ops.gemm(w[o + "wv"], h[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp)
-            qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((rows, 2 * d), torch.bfloat16), rows=rows, d=d, nseg=2,
-                                  ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
-            att = self._e((rows, d), torch.bfloat16)
-            ops.attention(qkr, qkr[:, d:], vt, att, B=B, H=H, Nq=Ntp, Nk=Ntp, ldq=2 * d, ldk=2 * d, ldvt=Ntp, ldo=d,
-                          q_bs=Ntp * 2 * d, k_bs=Ntp * 2 * d, vt_bs=d * Ntp, o_bs=Ntp * d, mask_bits=bits,
-                          mask_bs=words)
-            ops.gemm(att, w[o + "wo"], out=x, res1=x)
-            self._ffn(x, rows, d, w[o + "n2"], w[o + "w13"], w[o + "w2"])
-
-        # hoisted decoder K / V projections of the triangle tokens (view independent)
-        dv = cfg.view_transformer_latent_dim
-        k_pre, v_t = [], []
-        for i in range(cfg.view_transformer_n_layers):
-            o = f"dec{i}."
-            c = ops.rmsnorm(x, w[o + "n_kv"], self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
-            k_pre.append(ops.gemm(c, w[o + "wk"], out_dtype=torch.float32).view(B, Ntp, dv))
-            vt = self._e((B, dv, Ntp), torch.bfloat16)
-            for b in range(B):
-                ops.gemm(w[o + "wv"], c[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp)
-            v_t.append(vt)
-        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
+        return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8)
 
     def _encode_fused(self, x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8) -> SceneState:
         """Encoder + K/V hoist with RMSNorm fused into the GEMMs.  State carried between GEMMs:
@@ -282,17 +259,15 @@ class Engine:
             ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2)
             g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
             ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
-        k_pre, v_t = [], []
-        for i in range(cfg.view_transformer_n_layers):  # kv_norm is folded into wk / wv
-            o = f"dec{i}."
-            k_pre.append(ops.gemm(xb, w[o + "wk"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc if i == 0 else None,
-                                  **nrm).view(B, Ntp, dv))
-            vt = self._e((B, dv, Ntp), bf)
-            for b in range(B):
-                ops.gemm(w[o + "wv"], xb[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp,
-                         in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
-            v_t.append(vt)
-        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_pre, v_t)
+        # hoisted decoder K / V projections of the triangle tokens for ALL layers in two GEMMs
+        # (view independent; every layer's kv_norm weight is folded into its rows)
+        Lv = cfg.view_transformer_n_layers
+        k_all = ops.gemm(xb, w["dec.wk_all"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc, **nrm).view(B, Ntp, Lv * dv)
+        v_all = self._e((B, Lv * dv, Ntp), bf)
+        for b in range(B):
+            ops.gemm(w["dec.wv_all"], xb[b * Ntp:(b + 1) * Ntp], out=v_all[b], N=Ntp,
+                     in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
+        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_all, v_all, dv)
 
     def alloc_scene_state(self, B: int, N: int) -> SceneState:
         """Uninitialised SceneState of the right shapes (receive buffers for the NCCL broadcast)."""
@@ -304,8 +279,7 @@ class Engine:
         Lv = cfg.view_transformer_n_layers
         return SceneState(B, N, Nt, Ntp, self._e((B, Ntp, d), torch.float32), self._e((B, N, 9), torch.float32),
                           self._e((B, N), torch.uint8), self._e((B, words), torch.int32),
-                          [self._e((B, Ntp, dv), torch.float32) for _ in range(Lv)],
-                          [self._e((B, dv, Ntp), torch.bfloat16) for _ in range(Lv)])
+                          self._e((B, Ntp, Lv * dv), torch.float32), self._e((B, Lv * dv, Ntp), torch.bfloat16), dv)
 
     # ------------------------------------------------------------------ stage 2
     def _swin_maps(self, Hp, Wp, shift, V):
@@ -357,10 +331,10 @@ class Engine:
             qf = ops.gemm(h, w[o + "wq"], out_dtype=torch.float32)
             q = ops.qknorm_rope(qf, w[o + "qn"], self._e((rows, dv), bf), rows=rows, d=dv, nseg=1, ldx=dv, ldo=dv,
                                 eps=EPS)  # camera-space ray origin is 0: query RoPE is the identity (E5)
-            k = ops.qknorm_rope(st.k_pre[i][b], w[o + "kn"], self._e((V * Ntp, dv), bf), rows=V * Ntp, d=dv, nseg=1,
-                                ldx=dv, ldo=dv, in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
+            k = ops.qknorm_rope(st.k_pre(i, b), w[o + "kn"], self._e((V * Ntp, dv), bf), rows=V * Ntp, d=dv, nseg=1,
+                                ldx=st.k_all.shape[2], ldo=dv, in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
             att = self._e((rows, dv), bf)
-            ops.attention(q, k, st.v_t[i][b], att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
+            ops.attention(q, k, st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
                           q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0)
             ops.gemm(att, w[o + "wout"], out=x, res1=x)
 
@@ -420,9 +394,9 @@ class Engine:
             perm, region, inv = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
             # cross-attention: q = (n_q(x) Wq^T) . qn / rms  -- the 1/rms goes into the softmax scale
             ops.gemm(xb, w[o + "wq"], out16=qh, col_mul=w[o + "qn"], out_sumsq=qsq, in_sumsq=xsq, **nrm)
-            ops.qknorm_rope(st.k_pre[i][b], w[o + "kn"], kbuf, rows=V * Ntp, d=dv, nseg=1, ldx=dv, ldo=dv,
+            ops.qknorm_rope(st.k_pre(i, b), w[o + "kn"], kbuf, rows=V * Ntp, d=dv, nseg=1, ldx=st.k_all.shape[2], ldo=dv,
                             in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
-            ops.attention(qh, kbuf, st.v_t[i][b], att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
+            ops.attention(qh, kbuf, st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
                           q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0,
                           q_sumsq=qsq, sumsq_ld=P, sumsq_parts=P, **nrm)
             # x += out_proj(att); bf16 copy + row sums land in window order for the swin block

@@ -21,7 +21,7 @@ def _state(fill: bool) -> SceneState:
     mk = (lambda *s: torch.randn(*s, generator=g)) if fill else (lambda *s: torch.zeros(*s))
     return SceneState(1, 24, 40, 40, mk(1, 40, 64), mk(1, 24, 9),
                       (mk(1, 24) > 0).to(torch.uint8), (mk(1, 4) * 100).to(torch.int32),
-                      [mk(1, 40, 64) for _ in range(3)], [mk(1, 64, 40).to(torch.bfloat16) for _ in range(3)])
+                      mk(1, 40, 3 * 64), mk(1, 3 * 64, 40).to(torch.bfloat16), 64)
 
 
 def _worker(rank, world, port, q):
