@@ -1,8 +1,16 @@
 // Dense flash attention, second generation: two 128-query tiles per CTA sharing one K/V stream,
 // P kept in tensor memory.
 //
-//   warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax of query tile A,
-//   warps 6..9 = softmax of query tile B (one thread per query row).
+//   warpgroup 0: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-3 idle (they exist so
+//   that setmaxnreg can hand the group's registers to the softmax warpgroups);
+//   warpgroup 1 (warps 4-7) = softmax of query tile A, warpgroup 2 (warps 8-11) = softmax of query
+//   tile B, one thread per query row.
+//
+// The softmax is the co-critical resource next to the tensor pipe (128 x 128 exponentials per
+// 2 x 4.2 MFLOP tile pair: the 16/clk/SM MUFU rate equals the tensor time), so its inner loop uses
+// packed fp32x2 arithmetic (FFMA2 / FADD2) and evaluates a quarter of the exponentials with a
+// degree-3 polynomial on the FMA pipe (Cody-Waite split, exponent inserted with an integer add)
+// instead of MUFU.EX2.
 //
 // TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512).
 // After the softmax has pulled its whole S row into registers it writes P (bf16 pairs) back into
@@ -41,7 +49,27 @@ struct Attn2Params {
 constexpr uint32_t kT2 = 128 * 128 * 2;  // 128 x 128 bf16 tile
 constexpr uint32_t kH2 = 128 * 64 * 2;   // one 64-column swizzle half
 constexpr int kStg = 2;
-constexpr int kAttn2Threads = 64 + 2 * 128;
+constexpr int kAttn2Threads = 3 * 128;
+constexpr int kRegsWg0 = 56, kRegsSoftmax = 224;  // setmaxnreg targets (128*56 + 256*224 = 384*168)
+// every kPolyEvery-th pair of exponentials goes to the FMA-pipe polynomial (0 = all on MUFU)
+constexpr int kPolyEvery = 4;
+
+// 2^t for t in [-126, 0] on the FMA pipe, two lanes at a time: t = n + f, n = round(t), |f| <= 0.5,
+// 2^f ~ degree-3 minimax polynomial (rel. error 7.5e-5, far below bf16 resolution of P), and 2^n is
+// applied by adding n to the exponent field (r = t + 1.5*2^23 keeps n in its low mantissa bits).
+__device__ __forceinline__ void exp2_poly2(uint64_t t2, float& p0, float& p1) {
+  const float ta = fmaxf(lo2f(t2), -126.0f), tb = fmaxf(hi2f(t2), -126.0f);
+  const uint64_t t = pack2f(ta, tb);
+  const uint64_t magic = pack2f(12582912.0f, 12582912.0f);
+  const uint64_t r = fadd2(t, magic);
+  const uint64_t n = fadd2(r, pack2f(-12582912.0f, -12582912.0f));
+  const uint64_t f = ffma2(n, pack2f(-1.0f, -1.0f), t);
+  uint64_t p = ffma2(f, pack2f(0.0551716685f, 0.0551716685f), pack2f(0.2426111251f, 0.2426111251f));
+  p = ffma2(p, f, pack2f(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, pack2f(0.9999280572f, 0.9999280572f));
+  p0 = __uint_as_float(__float_as_uint(lo2f(p)) + (__float_as_uint(lo2f(r)) << 23));
+  p1 = __uint_as_float(__float_as_uint(hi2f(p)) + (__float_as_uint(hi2f(r)) << 23));
+}
 constexpr uint32_t kAttn2Smem = kT2 * (2 + 2 * kStg) + 1024 + 256;
 
 __global__ void __launch_bounds__(kAttn2Threads, 1)
@@ -92,6 +120,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
   const int vb = p.v_batched ? b : 0;
 
   if (warp == 0) {
+    setmaxnreg_dec<kRegsWg0>();
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * kT2);
       for (int t = 0; t < 2; ++t) {
@@ -112,6 +141,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
       }
     }
   } else if (warp == 1) {
+    setmaxnreg_dec<kRegsWg0>();
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
       auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T
@@ -163,9 +193,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
       umma_commit(&o_done[0]);
       umma_commit(&o_done[1]);
     }
+  } else if (warp < 4) {
+    setmaxnreg_dec<kRegsWg0>();  // idle warps of warpgroup 0
   } else {
     // ------------------------------ softmax warps ------------------------------
-    const int t = (warp - 2) >> 2;  // query tile of this warp group
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int t = (warp - 4) >> 2;  // query tile of this warp group
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -238,19 +271,27 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
       }
 
       // P = exp2(s*sl2 - m*sl2) -> bf16 pairs -> columns [0,64) of this tile's S region
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint64_t sl2_2 = pack2f(sl2, sl2), nms_2 = pack2f(neg_ms, neg_ms);
+      uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_f(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_ms));
-          const float p1 = ex2_f(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_ms));
-          rs4[i & 3] += p0 + p1;
+          const uint64_t t2 = ffma2(pack2f(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2_2, nms_2);
+          float p0, p1;
+          if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+            exp2_poly2(t2, p0, p1);
+          } else {
+            p0 = ex2_f(lo2f(t2)), p1 = ex2_f(hi2f(t2));
+          }
+          rs2[i & 3] = fadd2(rs2[i & 3], pack2f(p0, p1));
           pk[i] = pack_bf16(p0, p1);
         }
         tmem_st16(tS + c * 16, pk);
       }
+      const uint64_t rsum = fadd2(fadd2(rs2[0], rs2[1]), fadd2(rs2[2], rs2[3]));
+      float rs4[4] = {lo2f(rsum), hi2f(rsum), 0.f, 0.f};
       l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
 
@@ -314,6 +355,15 @@ int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
     if (cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=
         cudaSuccess)
       return RFB_ERR_LAUNCH;
+    // setmaxnreg moves registers inside the CTA's launch allocation only: the softmax warpgroups'
+    // request must be covered by what warpgroup 0 gives back, or the kernel would wait forever
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, attn2_tc_kernel) != cudaSuccess) return RFB_ERR_LAUNCH;
+    if (128 * kRegsWg0 + 256 * kRegsSoftmax > kAttn2Threads * fa.numRegs) {
+      fprintf(stderr, "rfb: attn2_tc_kernel compiled with %d registers/thread; setmaxnreg split %d/%d does not fit\n",
+              fa.numRegs, kRegsWg0, kRegsSoftmax);
+      return RFB_ERR_LAUNCH;
+    }
     attr_set = true;
   }
   dim3 grid((a->Nq + 255) / 256, a->H, a->B);

@@ -215,6 +215,50 @@ __device__ __forceinline__ void tmem_wait_st() {
 }
 
 // ----------------------------------------------------------------------------
+// register re-distribution between warpgroups (all 4 warps of a warpgroup execute it)
+// ----------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// ----------------------------------------------------------------------------
+// packed fp32x2 arithmetic (FFMA2 / FADD2: two fp32 lanes per issue slot)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo2f(uint64_t v) {
+  float lo, hi;
+  unpack2f(v, lo, hi);
+  return lo;
+}
+__device__ __forceinline__ float hi2f(uint64_t v) {
+  float lo, hi;
+  unpack2f(v, lo, hi);
+  return hi;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ----------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
