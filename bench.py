@@ -110,43 +110,52 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled with NVML every 20 ms from a thread while the
+    timed region runs (nvidia-smi's own loop is too coarse for a region of a few hundred ms)."""
 
     def __init__(self, index: int):
-        self.proc = None
+        import threading
+        self.rows, self.on, self.n = [], True, None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            self.n = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        n = self.n
+        while self.on:
+            try:
+                self.rows.append((n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM),
+                                  n.nvmlDeviceGetPowerUsage(self.h) / 1e3,
+                                  n.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])), mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.n is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.on = False
+        self.t.join(timeout=2)
+        n, rows = self.n, self.rows
+        names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap,
+                 "hw_power_brake": n.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": statistics.median(r[0] for r in rows) if rows else None, "sm_max_mhz": self.max,
+                "power_w_max": max((r[1] for r in rows), default=None), "samples": len(rows),
+                "reasons": sorted(k for k, v in names.items() if bits & v)}
 
 
 # --------------------------------------------------------------------------- GPU arm

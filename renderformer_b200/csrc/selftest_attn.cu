@@ -10,7 +10,7 @@ __global__ void ref_attn(const uint16_t* Q, long long ldq, long long qbs, const 
                          long long ldk, long long kbs, const uint16_t* Vt, long long ldvt,
                          long long vbs, float* O, int B, int H, int Nq, int Nk,
                          const uint32_t* mask, long long mstride, int mode, const uint8_t* gid,
-                         int period, float scale) {
+                         int period, float scale, const float* rq, const float* rk) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)B * H * Nq) return;
   const int qi = t % Nq, h = (t / Nq) % H, b = t / ((long long)Nq * H);
@@ -26,6 +26,8 @@ __global__ void ref_attn(const uint16_t* Q, long long ldq, long long qbs, const 
     float s = 0.f;
     for (int d = 0; d < 128; ++d) s = fmaf(bf2f(q[d]), bf2f(kr[d]), s);
     s *= scale;
+    if (rq) s *= rq[(long long)b * Nq + qi];
+    if (rk) s *= rk[(long long)b * Nk + k];
     const float mn = fmaxf(m, s);
     const float a = expf(m - mn), pexp = expf(s - mn);
     l = l * a + pexp;
@@ -40,6 +42,7 @@ __global__ void ref_attn(const uint16_t* Q, long long ldq, long long qbs, const 
 struct ACase {
   const char* name;
   int B, H, Nq, Nk, mode, masked, shareKV, period;
+  int fused = 0;  // 1: q_sumsq partial sums (fused q RMSNorm); 2: q and k sums (mode 1)
 };
 
 static void run(const ACase& c, bool timing_only = false) {
@@ -74,9 +77,30 @@ static void run(const ACase& c, bool timing_only = false) {
   DevBuf<uint8_t> dG(hg.size());
   dG.up(hg);
 
+  // fused QK-RMSNorm inputs: interleaved [q parts | k parts] partial sums per row, as rfb_gemm leaves them
+  const int parts = 3, sq_ld = 2 * parts, norm_dim = 384;
+  const float eps = 1e-6f;
+  const size_t nrows = (size_t)c.B * (c.Nq > c.Nk ? c.Nq : c.Nk);
+  std::vector<float> hsq(nrows * sq_ld), hrq(nrows, 1.f), hrk(nrows, 1.f);
+  for (size_t r = 0; r < nrows; ++r) {
+    float tq = 0.f, tk = 0.f;
+    for (int j = 0; j < parts; ++j) {
+      hsq[r * sq_ld + j] = 40.f + 80.f * (0.5f + 0.5f * hval(71, (uint32_t)(r * 8 + j)));
+      hsq[r * sq_ld + parts + j] = 30.f + 90.f * (0.5f + 0.5f * hval(72, (uint32_t)(r * 8 + j)));
+      tq += hsq[r * sq_ld + j], tk += hsq[r * sq_ld + parts + j];
+    }
+    hrq[r] = 1.0f / sqrtf(tq / norm_dim + eps), hrk[r] = 1.0f / sqrtf(tk / norm_dim + eps);
+  }
+  DevBuf<float> dsq(hsq.size()), drq(nrows), drk(nrows);
+  dsq.up(hsq), drq.up(hrq), drk.up(hrk);
+
   rfb_attn_args a;
   memset(&a, 0, sizeof(a));
   a.B = c.B, a.H = c.H, a.Nq = c.Nq, a.Nk = c.Nk;
+  if (c.fused) {
+    a.q_sumsq = dsq.p, a.sumsq_ld = sq_ld, a.sumsq_parts = parts, a.norm_dim = norm_dim, a.norm_eps = eps;
+    if (c.fused == 2) a.k_sumsq = dsq.p + parts;
+  }
   a.Q = dQ.p, a.ldq = D, a.q_batch_stride = (long long)c.Nq * D;
   a.K = dK.p, a.ldk = D, a.k_batch_stride = c.shareKV ? 0 : (long long)c.Nk * D;
   a.Vt = dV.p, a.ldvt = ldvt, a.vt_batch_stride = c.shareKV ? 0 : (long long)D * ldvt;
@@ -113,7 +137,7 @@ static void run(const ACase& c, bool timing_only = false) {
   ref_attn<<<(unsigned)((nthreads + 63) / 64), 64>>>(
       dQ.p, D, (long long)c.Nq * D, dK.p, D, a.k_batch_stride, dV.p, ldvt, a.vt_batch_stride, dref.p,
       c.B, c.H, c.Nq, c.Nk, c.masked ? dM.p : nullptr, words, c.mode, dG.p, c.period > 0 ? c.period : 1,
-      a.scale);
+      a.scale, c.fused ? drq.p : nullptr, c.fused == 2 ? drk.p : nullptr);
   CK(cudaDeviceSynchronize());
   std::vector<float> ref = dref.down();
   std::vector<uint16_t> ho = dO.down();
@@ -136,6 +160,8 @@ int main(int argc, char** argv) {
         {"enc-like B1 H8 N4112", 1, 8, 4112, 4112, 0, 1, 0, 0},
         {"swin mode1 B1 H2 N1024 period 256", 1, 2, 1024, 1024, 1, 0, 0, 256},
         {"swin mode1 B1 H8 N8192 period 4096", 1, 8, 8192, 8192, 1, 0, 0, 4096},
+        {"fused q-norm B3 H2 Nq300 Nk400 shared KV", 3, 2, 300, 400, 0, 1, 1, 0, 1},
+        {"fused q+k-norm swin mode1 B1 H2 N1024", 1, 2, 1024, 1024, 1, 0, 0, 256, 2},
     };
     for (auto& c : cases) run(c);
     printf("selftest_attn: %d failure(s)\n", g_fail);
