@@ -98,7 +98,19 @@ __global__ void rowstat_kernel(const float* __restrict__ x, void* __restrict__ o
 // pos[i / nfreq] * freq[i % nfreq], the remaining pairs are the identity.
 // Input row = r % in_period (lets V views re-rotate one shared pre-RoPE K), position row = r.
 // ---------------------------------------------------------------------------------------------
-__global__ void qknorm_rope_kernel(const float* __restrict__ x, long long ldx, int in_period,
+// sin/cos with an explicit two-constant reduction to [-pi, pi] followed by the SFU approximations
+// (abs. error ~1e-6 for the |angle| < 100 rad seen here; the result is rounded to bf16 anyway).
+// Keeps the kernels free of the slow-path code of sincosf and its register footprint.
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.28318548202514648f, x);
+  r = fmaf(k, 1.74845553146951715e-7f, r);
+  __sincosf(r, &s, &c);
+}
+
+// warp-per-row variant (no view fan-out): in_period == 0
+__global__ void __launch_bounds__(256, 3)
+    qknorm_rope_rows_kernel(const float* __restrict__ x, long long ldx, int in_period,
                                    const float* __restrict__ w, void* __restrict__ out, long long ldo,
                                    int rows, int d, int nseg, float eps, const float* __restrict__ pos,
                                    const float* __restrict__ freqs, int nfreq) {
@@ -115,11 +127,12 @@ __global__ void qknorm_rope_kernel(const float* __restrict__ x, long long ldx, i
     const int i = o + e;
     if (pos && i < 9 * nfreq) {
       const float ang = pos[(long long)row * 9 + i / nfreq] * __ldg(freqs + i % nfreq);
-      sincosf(ang, &sn[e], &cs[e]);
+      fast_sincos(ang, sn[e], cs[e]);
     }
   }
   const int units = d >> 3;  // (head, float4-pair) units per segment = H * 16
-  for (int s = 0; s < nseg; ++s) {
+  {
+    const int s = blockIdx.y;  // one (row, segment) per warp: twice the warps, no serial segment loop
     const float* xs = x + src * ldx + (long long)s * d;
     const float* ws = w + (long long)s * d;
     float4 lo[kMaxVec / 2], hi[kMaxVec / 2];
@@ -155,6 +168,85 @@ __global__ void qknorm_rope_kernel(const float* __restrict__ x, long long ldx, i
         const long long idx = (long long)row * ldo + (long long)s * d + base;
         store4_16(out, RFB_BF16, idx, ra[0], ra[1], ra[2], ra[3]);
         store4_16(out, RFB_BF16, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+      }
+    }
+  }
+}
+
+
+constexpr int kRopeViews = 4;  // views rotated per pass over one source row (= warps per block)
+
+__global__ void __launch_bounds__(kRopeViews * 32, 6)
+    qknorm_rope_kernel(const float* __restrict__ x, long long ldx, int in_period, const float* __restrict__ w,
+                       void* __restrict__ out, long long ldo, int rows, int d, int nseg, float eps,
+                       const float* __restrict__ pos, const float* __restrict__ freqs, int nfreq) {
+  // One block (4 warps) per SOURCE row.  With in_period > 0 the same source row feeds
+  // rows / in_period output rows (one per view, each with its own positions): warp v computes the
+  // rotation table of view v once into shared memory, then the warps split the row's segments and
+  // rotate each normalised segment for all views of the group from registers.
+  __shared__ float s_cs[kRopeViews][64], s_sn[kRopeViews][64];
+  const int src_rows = in_period > 0 ? in_period : rows;
+  const int nv = in_period > 0 ? rows / in_period : 1;
+  const int src = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = (lane & 15) * 4;  // pair offset inside a head (0..60)
+  const int units = d >> 3;       // (head, float4-pair) units per segment = H * 16
+
+  for (int v0 = 0; v0 < nv; v0 += kRopeViews) {
+    __syncthreads();
+    if (v0 + warp < nv) {
+      const long long row = (long long)(v0 + warp) * src_rows + src;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = lane * 2 + e;  // pair index 0..63
+        float c = 1.f, sn = 0.f;
+        if (pos && i < 9 * nfreq) fast_sincos(pos[row * 9 + i / nfreq] * __ldg(freqs + i % nfreq), sn, c);
+        s_cs[warp][i] = c, s_sn[warp][i] = sn;
+      }
+    }
+    __syncthreads();
+    for (int s = warp; s < nseg; s += kRopeViews) {
+      const float* xs = x + (long long)src * ldx + (long long)s * d;
+      const float* ws = w + (long long)s * d;
+      float4 lo[kMaxVec / 2], hi[kMaxVec / 2];
+      float ss = 0.f;
+#pragma unroll
+      for (int it = 0; it < kMaxVec / 2; ++it) {
+        const int u = it * 32 + lane;
+        if (u < units) {
+          const int base = (u >> 4) * 128 + o;
+          lo[it] = *reinterpret_cast<const float4*>(xs + base);
+          hi[it] = *reinterpret_cast<const float4*>(xs + base + 64);
+          ss += lo[it].x * lo[it].x + lo[it].y * lo[it].y + lo[it].z * lo[it].z + lo[it].w * lo[it].w;
+          ss += hi[it].x * hi[it].x + hi[it].y * hi[it].y + hi[it].z * hi[it].z + hi[it].w * hi[it].w;
+        }
+      }
+      ss = warp_sum(ss);
+      const float r = rsqrtf(ss / d + eps);
+#pragma unroll
+      for (int it = 0; it < kMaxVec / 2; ++it) {
+        const int u = it * 32 + lane;
+        if (u < units) {
+          const int base = (u >> 4) * 128 + o;
+          const float4 wl = __ldg(reinterpret_cast<const float4*>(ws + base));
+          const float4 wh = __ldg(reinterpret_cast<const float4*>(ws + base + 64));
+          const float a[4] = {lo[it].x * r * wl.x, lo[it].y * r * wl.y, lo[it].z * r * wl.z, lo[it].w * r * wl.w};
+          const float b[4] = {hi[it].x * r * wh.x, hi[it].y * r * wh.y, hi[it].z * r * wh.z, hi[it].w * r * wh.w};
+          for (int vv = 0; vv < kRopeViews && v0 + vv < nv; ++vv) {
+            const float4 c4 = *reinterpret_cast<const float4*>(&s_cs[vv][o]);
+            const float4 s4 = *reinterpret_cast<const float4*>(&s_sn[vv][o]);
+            const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+            float ra[4], rb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              ra[e] = a[e] * cs[e] - b[e] * sn[e];
+              rb[e] = b[e] * cs[e] + a[e] * sn[e];
+            }
+            const long long idx = ((long long)(v0 + vv) * src_rows + src) * ldo + (long long)s * d + base;
+            store4_16(out, RFB_BF16, idx, ra[0], ra[1], ra[2], ra[3]);
+            store4_16(out, RFB_BF16, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+          }
+        }
       }
     }
   }
@@ -393,7 +485,14 @@ extern "C" int rfb_qknorm_rope(const float* x, long long ldx, int in_period, con
     return RFB_ERR_ARG;
   if (pos && (!freqs || nfreq < 1 || 9 * nfreq > 64)) return RFB_ERR_ARG;
   const int wpb = 8;
-  qknorm_rope_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+  if (in_period > 0 && rows % in_period) return RFB_ERR_ARG;
+  const int src_rows = in_period > 0 ? in_period : rows;
+  if (in_period == 0) {
+    qknorm_rope_rows_kernel<<<dim3((rows + wpb - 1) / wpb, nseg), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq);
+    RFB_LAUNCHED("qknorm_rope_rows_kernel");
+  }
+  qknorm_rope_kernel<<<src_rows, kRopeViews * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq);
   RFB_LAUNCHED("qknorm_rope_kernel");
 }

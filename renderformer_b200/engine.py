@@ -162,6 +162,7 @@ class Engine:
             put(o + "w2", g(p + "ffn.w2.weight"), bf)
 
         Lv = cfg.view_transformer_n_layers
+        put("dec.kn_all", torch.cat([self.w.pop(f"dec{i}.kn") for i in range(Lv)], dim=0))
         put("dec.wk_all", torch.cat([self.w.pop(f"dec{i}.wk") for i in range(Lv)], dim=0))
         put("dec.wv_all", torch.cat([self.w.pop(f"dec{i}.wv") for i in range(Lv)], dim=0))
 
@@ -282,6 +283,16 @@ class Engine:
                           self._e((B, Ntp, Lv * dv), torch.float32), self._e((B, Lv * dv, Ntp), torch.bfloat16), dv)
 
     # ------------------------------------------------------------------ stage 2
+    def _keys_all_layers(self, st: SceneState, b: int, pos, V: int) -> torch.Tensor:
+        """K-side QK-RMSNorm + camera-space RoPE of the hoisted keys of EVERY decoder layer for V
+        views in one launch: bf16 [V*Ntp, L*dv]; layer i is the column slice [i*dv, (i+1)*dv)."""
+        cfg = self.cfg
+        dv, Lv = cfg.view_transformer_latent_dim, cfg.view_transformer_n_layers
+        kall = self._e((V * st.Ntp, Lv * dv), torch.bfloat16)
+        ops.qknorm_rope(st.k_all[b], self.w["dec.kn_all"], kall, rows=V * st.Ntp, d=dv, nseg=Lv, ldx=Lv * dv,
+                        ldo=Lv * dv, in_period=st.Ntp, pos=pos, freqs=self.w["dec.freqs"], eps=EPS)
+        return kall
+
     def _swin_maps(self, Hp, Wp, shift, V):
         key = (Hp, Wp, shift, V)
         if key not in self._maps:
@@ -324,6 +335,8 @@ class Engine:
         if self.fused_dec:
             return self._decode_fused(st, b, x, pos, V, Hp, Wp, taps)
         feats = []
+        Lv = cfg.view_transformer_n_layers
+        kall = self._keys_all_layers(st, b, pos, V)
         for i in range(cfg.view_transformer_n_layers):
             o = f"dec{i}."
             # cross-attention to the triangle tokens  (layers/attention.py:503-513)
@@ -331,11 +344,10 @@ class Engine:
             qf = ops.gemm(h, w[o + "wq"], out_dtype=torch.float32)
             q = ops.qknorm_rope(qf, w[o + "qn"], self._e((rows, dv), bf), rows=rows, d=dv, nseg=1, ldx=dv, ldo=dv,
                                 eps=EPS)  # camera-space ray origin is 0: query RoPE is the identity (E5)
-            k = ops.qknorm_rope(st.k_pre(i, b), w[o + "kn"], self._e((V * Ntp, dv), bf), rows=V * Ntp, d=dv, nseg=1,
-                                ldx=st.k_all.shape[2], ldo=dv, in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
             att = self._e((rows, dv), bf)
-            ops.attention(q, k, st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
-                          q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0)
+            ops.attention(q, kall[:, i * dv:], st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=Lv * dv,
+                          ldvt=Ntp, ldo=dv, q_bs=Nr * dv, k_bs=Ntp * Lv * dv, vt_bs=0, o_bs=Nr * dv,
+                          mask_bits=st.mask_bits[b], mask_bs=0)
             ops.gemm(att, w[o + "wout"], out=x, res1=x)
 
             # self-attention among ray tokens  (layers/attention.py:515-523)
@@ -386,7 +398,8 @@ class Engine:
         rsw = self._e((rows,), f32)
         att = self._e((rows, dv), bf)
         vt = self._e((dv, rows), bf)
-        kbuf = self._e((V * Ntp, dv), bf)
+        Lv = cfg.view_transformer_n_layers
+        kall = self._keys_all_layers(st, b, pos, V)
         ops.rowstat(x, xb, xsq, rows=rows, d=dv)
         feats = []
         for i in range(cfg.view_transformer_n_layers):
@@ -394,11 +407,9 @@ class Engine:
             perm, region, inv = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
             # cross-attention: q = (n_q(x) Wq^T) . qn / rms  -- the 1/rms goes into the softmax scale
             ops.gemm(xb, w[o + "wq"], out16=qh, col_mul=w[o + "qn"], out_sumsq=qsq, in_sumsq=xsq, **nrm)
-            ops.qknorm_rope(st.k_pre(i, b), w[o + "kn"], kbuf, rows=V * Ntp, d=dv, nseg=1, ldx=st.k_all.shape[2], ldo=dv,
-                            in_period=Ntp, pos=pos, freqs=w["dec.freqs"], eps=EPS)
-            ops.attention(qh, kbuf, st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=dv, ldvt=Ntp, ldo=dv,
-                          q_bs=Nr * dv, k_bs=Ntp * dv, vt_bs=0, o_bs=Nr * dv, mask_bits=st.mask_bits[b], mask_bs=0,
-                          q_sumsq=qsq, sumsq_ld=P, sumsq_parts=P, **nrm)
+            ops.attention(qh, kall[:, i * dv:], st.v_t(i, b), att, B=V, H=Hh, Nq=Nr, Nk=Ntp, ldq=dv, ldk=Lv * dv,
+                          ldvt=Ntp, ldo=dv, q_bs=Nr * dv, k_bs=Ntp * Lv * dv, vt_bs=0, o_bs=Nr * dv,
+                          mask_bits=st.mask_bits[b], mask_bs=0, q_sumsq=qsq, sumsq_ld=P, sumsq_parts=P, **nrm)
             # x += out_proj(att); bf16 copy + row sums land in window order for the swin block
             ops.gemm(att, w[o + "wout"], out=x, res1=x, out_sumsq=xsqw, out16=xbw, aux_row_map=inv)
             # shifted-window self-attention (window-major rows); q sums in parts [0,P), k sums in [P,2P)

@@ -153,7 +153,8 @@ def qknorm_rope(x, w, out, *, rows, d, nseg, ldx, ldo, in_period=0, pos=None, fr
     _need_cuda(x, w, out)
     nf = 0 if freqs is None else freqs.numel()
     L.check(_timed("qknorm_rope", 0.0, lambda: L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), ldo, rows, d,
-                                     nseg, eps, _p(pos), _p(freqs), nf, _stream())), "rfb_qknorm_rope")
+                                     nseg, eps, _p(pos), _p(freqs), nf, _stream()),
+                   f"rows={rows} d={d} nseg={nseg} period={in_period}"), "rfb_qknorm_rope")
     return out
 
 
