@@ -24,6 +24,8 @@ namespace rfb {
 
 extern std::atomic<long long> g_launch_count;
 
+int launch_attention_swin(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                          const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 
@@ -400,6 +402,13 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
       use_v2 = (e && e[0] == '1') ? 1 : 0;
     }
     if (!use_v2) return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
+  } else {
+    static int swin_v1 = -1;  // RFB_SWIN_V1=1: per-(tile, head) CTAs of attn_tc_kernel (A/B reference)
+    if (swin_v1 < 0) {
+      const char* e = getenv("RFB_SWIN_V1");
+      swin_v1 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!swin_v1) return launch_attention_swin(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
   }
 
   AttnKParams p{};
