@@ -289,9 +289,16 @@ def main():
         g = by.get("gemm", [0.0, 1.0, 1])
         att = by.get("attention", [0.0, 1.0, 1])
         ach = g[0] / g[1] / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01b_gemm_traffic.json")
+        if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, Vl) == (4096, 512, 4):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01b_gemm_traffic.json (ncu dram__bytes_read+write, avg over one step's GEMM launches)"
         roofline = {
             "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
-            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+            "traffic_source": traffic_src, "flop_per_launch": g[0] / g[2],
             "peak_source": peak_src, "launches_per_step": g[2], "avg_launch_us": g[1] / g[2] * 1e6,
             "share_of_step": g[1] * 1e3 / ms_step,
             "method": "per-launch CUDA events on the launch stream, one instrumented step after the timed region",

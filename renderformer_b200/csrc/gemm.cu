@@ -67,6 +67,11 @@ constexpr uint32_t kABytes = kBM * kBK * 2;
 // 32 x 32 fp32 transposition buffer (16-byte chunks XOR-swizzled by row, no padding)
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+// EK_RESID variant: warpgroup 0 = {TMA, MMA, 2 idle warps}, warpgroups 1-2 = epilogue; setmaxnreg hands
+// warpgroup 0's registers to the epilogue warps so that the residual of a warp's whole half tile
+// (4 chunks x 8 row slots x 16 B) can be in flight while the main loop of the tile is still running.
+constexpr int kGemmThreadsWG = 128 + kEpiWarps * 32;
+constexpr int kRegsGemmWg0 = 56, kRegsGemmEpi = 224;  // 128*56 + 256*224 = 384*168
 constexpr uint32_t kEpiStageBytes = kEpiWarps * 32 * 32 * 4;
 
 template <int BN>
@@ -433,13 +438,17 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
   const float* res = static_cast<const float*>(p.res1);
   float* out = static_cast<float*>(p.out);
   uint16_t* out16 = static_cast<uint16_t*>(p.out16);
-  uint4 ra[8], rb[8];
-  auto prefetch = [&](uint4(&r)[8], int n) {
+  // the residual of the whole half tile is requested up front (register budget: setmaxnreg), so
+  // its latency hides behind the main loop of this tile
+  uint4 rr4[4][8];
+  if (RES) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it)
-      if (orow[it] >= 0) r[it] = *reinterpret_cast<const uint4*>(res + (long long)orow[it] * p.ldres + n);
-  };
-  if (RES) prefetch(ra, n_begin + c4 * 4);
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (orow[it] >= 0)
+          rr4[c][it] = *reinterpret_cast<const uint4*>(res + (long long)orow[it] * p.ldres + n_begin + c * 32 + c4 * 4);
+  }
   mbar_wait(tfull_bar, parity);
   tc_fence_after();
 #pragma unroll
@@ -447,10 +456,6 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
     uint32_t v[32];
     tmem_ld32(taddr + c * 32, v);
     const int n = n_begin + c * 32 + c4 * 4;
-    if (RES && c + 1 < 4) {
-      if (c & 1) prefetch(ra, n + 32);
-      else prefetch(rb, n + 32);
-    }
     float cm[4] = {1.f, 1.f, 1.f, 1.f};
     if (!RES) load4(p.col_mul, RFB_F32, n, cm);
     tmem_wait_ld();
@@ -466,12 +471,16 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
       const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c4 ^ (rr & 7)) << 2));
       float x[4] = {a.x * rs[it], a.y * rs[it], a.z * rs[it], a.w * rs[it]};
       if (RES) {
-        const uint4& r = (c & 1) ? rb[it] : ra[it];
+        const uint4& r = rr4[c][it];
         x[0] += __uint_as_float(r.x), x[1] += __uint_as_float(r.y);
         x[2] += __uint_as_float(r.z), x[3] += __uint_as_float(r.w);
       }
       if (orow[it] >= 0) {
-        if (RES) *reinterpret_cast<float4*>(out + (long long)orow[it] * p.ldo + n) = make_float4(x[0], x[1], x[2], x[3]);
+        if (RES) {
+          const uint4 xo = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]),
+                                      __float_as_uint(x[3]));
+          *reinterpret_cast<uint4*>(out + (long long)orow[it] * p.ldo + n) = xo;
+        }
         sqp[it] += x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
         uint2 u;
         u.x = pack_bf16(x[0] * cm[0], x[1] * cm[1]), u.y = pack_bf16(x[2] * cm[2], x[3] * cm[3]);
@@ -496,7 +505,7 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
 
 
 template <int BN, int EK>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int EPI0 = (EK == EK_RESID) ? 4 : 2;  // first epilogue warp
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -544,6 +554,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
+    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -579,6 +590,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -603,8 +615,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         umma_commit(&tfull[as]);  // accumulator complete -> epilogue
       }
     }
+  } else if (warp < EPI0) {
+    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();  // idle warps of warpgroup 0
   } else {
     // ------------------------------ epilogue ------------------------------
+    if constexpr (EK == EK_RESID) setmaxnreg_inc<kRegsGemmEpi>();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     int it = 0;
@@ -646,16 +661,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             for (int j = 0; j < p.in_sumsq_parts; ++j) ss += sp[j];
           }
           rs = rsqrtf(ss * p.inv_norm_dim + p.norm_eps);
-          if (p.out_rscale && n0 == 0 && warp < 6) p.out_rscale[mt * kBM + r] = rs;
+          if (p.out_rscale && n0 == 0 && warp < EPI0 + 4) p.out_rscale[mt * kBM + r] = rs;
         } else if (p.in_rscale && p.scale_dim == 0) {
           rs = p.in_rscale[mt * kBM + r];
         }
       }
-      float* my_stage = epi_stage + (warp - 2) * 32 * 32;
+      float* my_stage = epi_stage + (warp - EPI0) * 32 * 32;
       // the two warps of a TMEM lane quarter take the two contiguous halves of the tile's columns
       constexpr int NCH = BN / 32;
       constexpr int HALF = (NCH + 1) / 2;
-      const int c_begin = ((warp - 2) >> 2) * HALF;
+      const int c_begin = ((warp - EPI0) >> 2) * HALF;
       const int c_end = (c_begin + HALF < NCH) ? c_begin + HALF : NCH;
       if constexpr (EK != EK_GENERIC) {
         static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
@@ -703,9 +718,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (cudaFuncSetAttribute(gemm_tc_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmemBytes) != cudaSuccess)
       return RFB_ERR_LAUNCH;
+    if (EK == EK_RESID) {  // setmaxnreg only moves registers inside the CTA's launch allocation
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BN, EK>) != cudaSuccess) return RFB_ERR_LAUNCH;
+      if (128 * kRegsGemmWg0 + 256 * kRegsGemmEpi > kGemmThreadsWG * fa.numRegs) {
+        fprintf(stderr, "rfb: gemm_tc_kernel<RESID> compiled with %d registers/thread; setmaxnreg split does not fit\n",
+                fa.numRegs);
+        return RFB_ERR_LAUNCH;
+      }
+    }
     attr_set = true;
   }
-  gemm_tc_kernel<BN, EK><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  constexpr int threads = (EK == EK_RESID) ? kGemmThreadsWG : kGemmThreads;
+  gemm_tc_kernel<BN, EK><<<grid, threads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   g_launch_count++;
   return check_launch("gemm_tc_kernel");
 }
