@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--torch-cuda", action="store_true",
+                    help="also time the oracle port on cuda:0 with torch kernels under bf16 autocast "
+                         "(context: what the reference's PyTorch CUDA path costs on this GPU)")
     return ap.parse_args()
 
 
@@ -314,6 +317,32 @@ def main():
         fps, ms, cores, sample = cpu_sample(args.config, 2, 1, N, R, Vl)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    torch_cuda = None
+    if rank == 0 and world == 1 and args.torch_cuda:
+        # context only: the reference's algorithm executed by torch's own CUDA kernels (SDPA, cuBLAS,
+        # cuDNN) on this GPU.  The unmodified reference cannot travel to the GPU box (it imports
+        # roma / needs /root/reference), so this is the oracle port under bf16 autocast -- a checker
+        # being timed beside the product, never on the product path.
+        from oracle import renderformer_oracle as orc
+        sd_gpu = {k: v.to(dev) for k, v in init_state_dict(cfg, 7).items()}
+        g_in = {k: v.to(dev) for k, v in scene.items()}
+
+        def torch_step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return orc.render(sd_gpu, cfg, g_in["triangles"], g_in["texture"], g_in["mask"], g_in["vn"],
+                                  g_in["c2w"], g_in["fov"], R, view_chunk=Vl)
+        try:
+            for _ in range(2):
+                torch_step()
+            ms_t = timed(torch_step, max(2, min(args.steps, 5)))
+            torch_cuda = {"value": frames / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t, "kind": "port",
+                          "what": "oracle (functional restatement of the reference) on cuda:0, torch SDPA/cuBLAS/cuDNN "
+                                  "kernels, bf16 autocast, K/V recomputed per view like the reference"}
+        except Exception as e:  # noqa: BLE001
+            torch_cuda = {"unavailable": repr(e)[:200]}
+        del sd_gpu, g_in
+        torch.cuda.empty_cache()
+
     if rank == 0:
         step_tflop = job_flops(cfg, N, R, 1, frames) / 1e12
         line = {
@@ -331,6 +360,8 @@ def main():
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if torch_cuda is not None:
+            line["torch_cuda_port"] = torch_cuda
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
