@@ -26,6 +26,8 @@ extern std::atomic<long long> g_launch_count;
 
 int launch_attention_swin(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
+int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_attn_args* a, int k_batched,
+                      int v_batched, cudaStream_t stream);
 int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 
@@ -396,12 +398,13 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
   }
 
   if (a->mode == 0) {
-    static int use_v2 = -1;
-    if (use_v2 < 0) {
-      const char* e = getenv("RFB_ATTN_V2");
-      use_v2 = (e && e[0] == '1') ? 1 : 0;
+    static int gen = -1;  // RFB_ATTN_GEN = 1 | 2 | 3 selects the dense kernel generation (default 3)
+    if (gen < 0) {
+      const char* e = getenv("RFB_ATTN_GEN");
+      gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
     }
-    if (!use_v2) return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
+    if (gen == 3) return launch_attention3(tmK, tmV, a, k_batched, v_batched, stream);
+    if (gen == 2) return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
   } else {
     static int swin_v1 = -1;  // RFB_SWIN_V1=1: per-(tile, head) CTAs of attn_tc_kernel (A/B reference)
     if (swin_v1 < 0) {
