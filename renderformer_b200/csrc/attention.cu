@@ -398,10 +398,21 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
   }
 
   if (a->mode == 0) {
-    static int gen = -1;  // RFB_ATTN_GEN = 1 | 2 | 3 selects the dense kernel generation (default 3)
-    if (gen < 0) {
+    static int forced = -1;  // RFB_ATTN_GEN = 1 | 2 | 3 forces one dense kernel generation (A/B runs)
+    if (forced < 0) {
       const char* e = getenv("RFB_ATTN_GEN");
-      gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
+      forced = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
+    }
+    int gen = forced;
+    if (gen == 0) {
+      // Both kernels sustain the same rate per tile; what differs is how evenly their grids fill
+      // the SMs (one CTA per SM): two-tile CTAs (gen 2) vs one-tile CTAs (gen 3).
+      const int sms = num_sms();
+      const long long n2 = (long long)((a->Nq + 255) / 256) * a->H * a->B;
+      const long long n3 = (long long)((a->Nq + 127) / 128) * a->H * a->B;
+      const double e2 = (double)n2 / (double)(((n2 + sms - 1) / sms) * sms);
+      const double e3 = (double)n3 / (double)(((n3 + sms - 1) / sms) * sms);
+      gen = (e3 > e2 + 0.02) ? 3 : 2;
     }
     if (gen == 3) return launch_attention3(tmK, tmV, a, k_batched, v_batched, stream);
     if (gen == 2) return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
