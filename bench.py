@@ -270,7 +270,30 @@ def main():
         h2d = sum(host[k].numel() * host[k].element_size() for k in ("triangles", "texture", "mask", "vn"))
         h2d += world * (host["c2w_local"].numel() + host["fov_local"].numel()) * 4
         e2e = {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(world * out_host.numel() * 4)}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(world * out_host.numel() * 4),
+               "api": "RenderFormerRenderingPipeline.render, one blocking call per step"}
+        if world == 1:
+            # the batch API (batch_infer.py use case): every step still uploads its own inputs from
+            # pinned host memory and downloads its own images inside the timed region, but the upload
+            # of step i+1 and the download of step i overlap the kernels of the neighbouring step
+            host_scene = {"triangles": host["triangles"], "texture": host["texture"], "mask": host["mask"],
+                          "vn": host["vn"], "c2w": host["c2w_local"], "fov": host["fov_local"]}
+
+            def stream_steps(n):
+                sink = 0.0
+                for img in pipe.render_stream((host_scene for _ in range(n)), resolution=R,
+                                              torch_dtype=torch.bfloat16):
+                    sink += float(img[0, 0, 0, 0, 0])  # touch the host result of every step
+                return sink
+
+            stream_steps(3)
+            ms_stream = timed(lambda: stream_steps(args.steps), 1) / args.steps
+            e2e = {"value": frames / (ms_stream * 1e-3), "unit": UNIT, "ms_per_step": ms_stream,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                   "api": "RenderFormerRenderingPipeline.render_stream (host scenes in, pinned host images out; "
+                          "copies of neighbouring steps overlap the kernels)",
+                   "single_call": {"value": frames / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
+                                   "api": "RenderFormerRenderingPipeline.render, one blocking call per step"}}
 
     roofline = None
     if not args.no_roofline and rank == 0:

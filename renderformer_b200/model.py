@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from .config import RenderFormerConfig
+from . import lib as L
 from .engine import Engine, SceneState
 from .synth import state_dict_shapes
 
@@ -161,3 +162,56 @@ class RenderFormerRenderingPipeline:
 
     def __call__(self, *args, **kwargs):
         return self.render(*args, **kwargs)
+
+    @torch.no_grad()
+    def render_stream(self, scenes, resolution: int = 512, torch_dtype: torch.dtype = torch.float16):
+        """Render a sequence of scenes given as HOST tensors (the batch_infer.py use case,
+        batch_infer.py:103-143): generator over dicts with the keys of `render` ('triangles', 'texture',
+        'mask', 'vn', 'c2w', 'fov'), yielding one pinned-host fp32 HDR tensor [B,V,H,W,3] per scene,
+        in order.
+
+        The host->device copy of scene i+1 (218 MB of texture for 4096 triangles) runs on a copy
+        stream while scene i is being rendered, and the device->host copy of image i overlaps scene
+        i+1; pass pinned tensors for truly asynchronous copies.  A yielded buffer belongs to a ring
+        of three and is overwritten two scenes later -- copy it if it must live longer."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise L.RfbError("render_stream needs a CUDA device (there is no CPU fallback)")
+        keys = ("triangles", "texture", "mask", "vn", "c2w", "fov")
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+
+        def upload(sc):
+            with torch.cuda.stream(copy):
+                d = {k: sc[k].to(dev, non_blocking=True) for k in keys}
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return d, ev
+
+        it = iter(scenes)
+        first = next(it, None)
+        pending = upload(first) if first is not None else None
+        ring, slot, prev = [None, None, None], 0, None
+        while pending is not None:
+            d, ev = pending
+            nxt = next(it, None)
+            pending = upload(nxt) if nxt is not None else None  # overlaps with this scene's kernels
+            main.wait_event(ev)
+            img = self.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"],
+                              resolution=resolution, torch_dtype=torch_dtype)
+            for t in d.values():
+                t.record_stream(main)  # allocated on the copy stream, consumed on the main stream
+            if ring[slot] is None or ring[slot].shape != img.shape:
+                ring[slot] = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+            host = ring[slot]
+            slot = (slot + 1) % 3
+            host.copy_(img, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if prev is not None:
+                prev[1].synchronize()
+                yield prev[0]
+            prev = (host, done)
+        if prev is not None:
+            prev[1].synchronize()
+            yield prev[0]

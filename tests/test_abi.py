@@ -58,6 +58,8 @@ def test_product_path_has_no_cpu_fallback():
     sc = make_scene(8, 1)
     with pytest.raises(lib.RfbError):
         pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=64)
+    with pytest.raises(lib.RfbError):
+        list(pipe.render_stream(iter([sc]), resolution=64))
 
 
 def test_product_does_not_import_oracle():

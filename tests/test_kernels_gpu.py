@@ -17,11 +17,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("binary,arg", [("selftest_gemm", "check"), ("selftest_attn", "check")])
-def test_kernel_selftests(binary, arg):
+@pytest.mark.parametrize("binary,env", [
+    ("selftest_gemm", {}),
+    ("selftest_attn", {}),                       # kernel generation picked per shape
+    ("selftest_attn", {"RFB_ATTN_GEN": "2"}),    # two query tiles per CTA
+    ("selftest_attn", {"RFB_ATTN_GEN": "3"}),    # one query tile per CTA, Q in TMEM
+    ("selftest_attn", {"RFB_ATTN_GEN": "1", "RFB_SWIN_V1": "1"}),  # first-generation reference kernel
+])
+def test_kernel_selftests(binary, env):
     exe = os.path.join(ROOT, "renderformer_b200", binary)
     assert os.path.exists(exe), f"{exe} missing: run __graft_entry__.build()"
-    r = subprocess.run([exe, arg], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=600, env={**os.environ, **env})
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-2000:]
     assert "0 failure(s)" in r.stdout, tail
@@ -80,3 +86,23 @@ def test_swin_rejects_bad_resolution():
     sc = {k: v.cuda() for k, v in make_scene(16, 1, seed=1).items()}
     with pytest.raises(ValueError):
         pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=96)
+
+
+def test_render_stream_matches_blocking_calls():
+    """The overlapped host-in / host-out batch API returns exactly what one blocking render() per
+    scene returns, in order, for scenes of different sizes."""
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, _ = _pipe(cfg, 9)
+    scenes = [make_scene(n, v, seed=s, pad_to=p) for n, v, s, p in ((40, 2, 1, 48), (70, 1, 2, None), (40, 2, 3, 48),
+                                                                     (16, 3, 4, None), (90, 1, 5, 96))]
+    host = [{k: t.pin_memory() for k, t in sc.items()} for sc in scenes]
+    want = []
+    for sc in scenes:
+        g = {k: t.cuda() for k, t in sc.items()}
+        want.append(pipe(g["triangles"], g["texture"], g["mask"], g["vn"], g["c2w"], g["fov"], resolution=64).cpu())
+    got = [img.clone() for img in pipe.render_stream(iter(host), resolution=64)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and a.is_pinned() is False  # clones of the pinned ring buffers
+        assert torch.equal(a, b)
+    assert list(pipe.render_stream(iter([]), resolution=64)) == []
