@@ -181,6 +181,13 @@ int rfb_token_assemble(const float* a, const float* wa, const float* b, const fl
 int rfb_texture_prep(const float* tex, void* out, long long n_tris, int channels, int texels,
                      int log_channels, rfb_stream_t stream);
 
+/* Constant-texture fast path: scenes written by scene_processor/to_h5.py:37-66 hold
+ * 13 per-triangle constants times a fixed triangular texel mask, so texture_encoder
+ * (models/renderformer.py:145-147) collapses to a [N,13] x [13,d] product with the texel-summed weight.
+ * tex fp32 [n_tris, channels] -> f16 [n_tris, ld] zero padded, log10(x+1) on the last log_channels. */
+int rfb_texture_const_prep(const float* tex, void* out, long long n_tris, int channels, int ld, int log_channels,
+                           rfb_stream_t stream);
+
 /* NeRF encoding of vertex normals [n,9] -> f16 [n, ld] (encodings/nerf_encoding.py:63-84). */
 int rfb_vn_encode(const float* vn, void* out, int n, int nfreq, int ld, rfb_stream_t stream);
 

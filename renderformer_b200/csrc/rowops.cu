@@ -325,6 +325,22 @@ __global__ void texture_prep_kernel(const float* __restrict__ tex, uint16_t* __r
   }
 }
 
+// per-triangle constant texture [n, C] fp32 -> f16 [n, ld] (zero padded), log10(x+1) on the last
+// `log_channels` channels: the input of the reduced texture projection (constant-texture fast path)
+__global__ void texture_const_prep_kernel(const float* __restrict__ tex, uint16_t* __restrict__ out, long long n,
+                                          int channels, int ld, int log_channels) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ld) return;
+  const long long row = t / ld;
+  const int c = (int)(t % ld);
+  float v = 0.f;
+  if (c < channels) {
+    v = tex[row * channels + c];
+    if (c >= channels - log_channels) v = log10f(v + 1.f);
+  }
+  out[t] = __half_as_ushort(__float2half_rn(v));
+}
+
 // vertex normals [n, 9] -> NeRF encoding [n, 128] f16 (117 used: x | sin(x 2^j) | cos(x 2^j), zero pad)
 //   encodings/nerf_encoding.py:63-84 with F frequencies, input-major / frequency-minor order.
 __global__ void vn_encode_kernel(const float* __restrict__ vn, uint16_t* __restrict__ out, int n, int nf,
@@ -518,6 +534,16 @@ extern "C" int rfb_texture_prep(const float* tex, void* out, long long n_tris, i
   texture_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tex, (uint16_t*)out, n, per,
                                                                 (channels - log_channels) * texels / 4);
   RFB_LAUNCHED("texture_prep_kernel");
+}
+
+extern "C" int rfb_texture_const_prep(const float* tex, void* out, long long n_tris, int channels, int ld,
+                                      int log_channels, rfb_stream_t stream) {
+  if (!tex || !out || n_tris <= 0 || channels <= 0 || ld < channels || ld % 8 || log_channels > channels)
+    return RFB_ERR_ARG;
+  const long long total = n_tris * ld;
+  texture_const_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      tex, (uint16_t*)out, n_tris, channels, ld, log_channels);
+  RFB_LAUNCHED("texture_const_prep_kernel");
 }
 
 extern "C" int rfb_vn_encode(const float* vn, void* out, int n, int nfreq, int ld, rfb_stream_t stream) {

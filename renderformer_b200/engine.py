@@ -128,6 +128,16 @@ class Engine:
         vwp[:, : vw.shape[1]] = vw
         put("vn.w", vwp, hf), put("vn.b", g("vn_encoding_proj.bias")), put("vn.norm", g("vn_encoder_norm.weight"))
         put("tex.w", g("texture_encoder.weight"), hf), put("tex.b", g("texture_encoder.bias"))
+        # constant-texture fast path: texels of one channel share one value inside the triangular
+        # texel mask x + y <= P, so the projection reduces to the texel-summed weight [d, channels]
+        P_, C_ = cfg.texture_encode_patch_size, cfg.texture_channels
+        ii = torch.arange(P_, device=dev)
+        tmask = (ii[:, None] + ii[None, :] <= P_).to(torch.float32)
+        wr = (g("texture_encoder.weight").view(d, C_, P_, P_) * tmask).sum(dim=(2, 3))
+        self.texc_ld = _rup(C_, 16)
+        wrp = torch.zeros((d, self.texc_ld), device=dev)
+        wrp[:, :C_] = wr
+        put("tex.wr", wrp, hf)
         put("tex.norm", g("texture_encoder_norm.weight"))
         put("enc.freqs", g("transformer.rope_emb.freqs"))
         for i in range(cfg.num_layers):
@@ -208,13 +218,22 @@ class Engine:
         tri = triangles.reshape(B, N, 9).to(dev, torch.float32).contiguous()
         vn9 = vn.reshape(B, N, 9).to(dev, torch.float32).contiguous()
         tex = texture.to(dev, torch.float32).contiguous()
+        const_tex = tex.dim() == 3  # [B, N, channels]: per-triangle constants (scene_io / to_h5 scenes)
         mask_u8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8)
         C_, P = cfg.texture_channels, cfg.texture_encode_patch_size
 
         # token construction  (models/renderformer.py:126-169)
-        tex16 = ops.texture_prep(tex, self._e((B * N, C_ * P * P), torch.float16), n_tris=B * N, channels=C_,
-                                 texels=P * P, log_channels=0 if (cfg.use_ldr or texture_is_log) else 3)
-        tex_lin = ops.gemm(tex16, w["tex.w"], bias=w["tex.b"], out_dtype=torch.float32)
+        log_ch = 0 if (cfg.use_ldr or texture_is_log) else 3
+        if const_tex:
+            if tex.shape[2] != C_:
+                raise ValueError(f"constant texture must be [B, N, {C_}], got {tuple(tex.shape)}")
+            tex16 = ops.texture_const_prep(tex, self._e((B * N, self.texc_ld), torch.float16), n_tris=B * N,
+                                           channels=C_, ld=self.texc_ld, log_channels=log_ch)
+            tex_lin = ops.gemm(tex16, w["tex.wr"], bias=w["tex.b"], out_dtype=torch.float32)
+        else:
+            tex16 = ops.texture_prep(tex, self._e((B * N, C_ * P * P), torch.float16), n_tris=B * N, channels=C_,
+                                     texels=P * P, log_channels=log_ch)
+            tex_lin = ops.gemm(tex16, w["tex.w"], bias=w["tex.b"], out_dtype=torch.float32)
         del tex16
         vn16 = ops.vn_encode(vn9, self._e((B * N, self.vn_ld), torch.float16), n=B * N, nfreq=cfg.vn_pe_num_freqs,
                              ld=self.vn_ld)

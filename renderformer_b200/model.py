@@ -151,6 +151,11 @@ class RenderFormerRenderingPipeline:
         """triangles [B,N,3,3], texture [B,N,13,32,32], mask [B,N] bool, vn [B,N,3,3], c2w [B,V,4,4],
         fov [B,V,1] degrees -> HDR [B,V,H,W,3] fp32.
 
+        `texture` may also be [B,N,13]: per-triangle constants (what scene_processor/to_h5.py:37-66
+        expands to the 32x32 texel grid with a fixed triangular mask).  The texture projection then
+        uses texel-summed weights -- no 218 MB texel grid has to exist or be uploaded
+        (`renderformer_b200.scene_io.to_pipeline_inputs(..., constant_texture=True)`).
+
         `torch_dtype` is accepted for source compatibility and validated like the reference
         (rendering_pipeline.py:98); the engine has a single precision policy (bf16/fp16 tensor-core
         operands, fp32 accumulation) and always returns fp32.  Unlike the reference (:68) the

@@ -172,6 +172,13 @@ def texture_prep(tex, out, *, n_tris, channels, texels, log_channels=3):
     return out
 
 
+def texture_const_prep(tex, out, *, n_tris, channels, ld, log_channels):
+    _need_cuda(tex, out)
+    L.check(_timed("texture_const_prep", 0.0, lambda: L.load().rfb_texture_const_prep(
+        tex.data_ptr(), out.data_ptr(), n_tris, channels, ld, log_channels, _stream())), "rfb_texture_const_prep")
+    return out
+
+
 def vn_encode(vn, out, *, n, nfreq, ld):
     _need_cuda(vn, out)
     L.check(_timed("vn_encode", 0.0, lambda: L.load().rfb_vn_encode(vn.data_ptr(), out.data_ptr(), n, nfreq, ld, _stream())), "rfb_vn_encode")
