@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from Python (N=1 only)")
     ap.add_argument("--torch-cuda", action="store_true",
                     help="also time the oracle port on cuda:0 with torch kernels under bf16 autocast "
                          "(context: what the reference's PyTorch CUDA path costs on this GPU)")
@@ -209,9 +210,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphs = world == 1 and not args.no_cuda_graphs
+
     def step_device(inp):
         """Both stages with inputs resident in HBM; returns this rank's images."""
         if world == 1:
+            if pipe.cuda_graphs:  # one CUDA-graph replay of the whole call (inputs copied into its static buffers)
+                return pipe.render(inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w_local"],
+                                   inp["fov_local"], resolution=R, torch_dtype=torch.bfloat16)
             st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"])
         else:
             st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"]) if rank == 0 \
@@ -252,12 +258,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
 
+    pipe.cuda_graphs = graphs
     for _ in range(max(args.warmup, 3)):
         step_device(d_in)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = lib.launch_count()
+    launches0 = lib.launch_count() + pipe.replayed_launches
     ms_step = timed(lambda: step_device(d_in), args.steps)
-    launches = (lib.launch_count() - launches0)
+    launches = (lib.launch_count() + pipe.replayed_launches - launches0)
     clocks = sampler.stop() if sampler else None
     frames = Vl * world
     value = frames / (ms_step * 1e-3)
@@ -298,6 +305,7 @@ def main():
     roofline = None
     if not args.no_roofline and rank == 0:
         peak_tf, _, peak_src = load_peaks()
+        pipe.cuda_graphs = False  # per-launch events need eager launches
         ops.PROFILE = []
         torch.cuda.synchronize()
         step_device(d_in) if world == 1 else (pipe.render_views(
@@ -305,6 +313,7 @@ def main():
             d_in["fov_local"], R))
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        pipe.cuda_graphs = graphs
         by = {}
         for kind, fl, a, b, _tag in prof:
             t = a.elapsed_time(b) * 1e-3
@@ -377,6 +386,7 @@ def main():
                             f"{Vl} views/GPU per step ({frames} views total; 32-view batch at 8 GPUs = BASELINE configs[2]); "
                             "scene stage once per step on rank 0 + NCCL broadcast of per-layer K/V",
                 "l2": "inputs + weights (~1.3 GB per step) exceed the 126 MB L2; no explicit flush",
+                "launch": ("one CUDA-graph replay per step (pipeline.cuda_graphs)" if graphs else "eager launches from Python"),
                 "algorithmic_tflop_per_step": step_tflop,
                 "model_flops_utilisation": step_tflop / (ms_step * 1e-3) / world / load_peaks()[0],
                 "scene_tflop": scene_flops(cfg, N) / 1e12, "view_tflop": view_flops(cfg, N, R) / 1e12,

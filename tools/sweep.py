@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--views", type=int, default=4)
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--config", default="v1_1_swin_large")
+ap.add_argument("--eager", action="store_true", help="launch from Python instead of CUDA-graph replay")
 a = ap.parse_args()
 peak = 1414.1
 pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -30,6 +31,9 @@ model.load_state_dict(init_state_dict(cfg, 7))
 pipe = RenderFormerRenderingPipeline(model)
 pipe.to(torch.device("cuda:0"))
 pipe.view_chunk = a.views
+pipe.cuda_graphs = not a.eager
+pipe.max_cached_graphs = 1
+print(f"launch mode: {'eager' if a.eager else 'CUDA-graph replay'}\n")
 print(f"| triangles | resolution | ray tokens/view | ms/step ({a.views} views) | frames/s | TFLOP/step | TFLOP/s | frac of {peak:.0f} |")
 print("|---|---|---|---|---|---|---|---|")
 for n in (512, 1024, 2048, 4096):
