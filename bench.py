@@ -25,6 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL writes its debug / version banner to stdout by default; the contract is ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 METRIC = "frames/sec (512^2, 4096 tris)"
