@@ -214,6 +214,12 @@ int rfb_im2col_s2(const void* in, void* out, int B, int H, int W, int C, rfb_str
 int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
                           rfb_stream_t stream);
 
+/* HDR fp32 [n_pixels, 3] -> uint8 [n_pixels, 3], the step right after the path in the CLIs
+ * (infer.py:94-98, batch_infer.py:153-157).  mode 0 = their default `(np.clip(hdr, 0, 1) * 255).astype(uint8)`,
+ * bit-exact; mode 1 = Khronos PBR Neutral tone curve + sRGB OETF (published formula; the reference reaches
+ * it through simple_ocio, which is not vendored: unpinned). */
+int rfb_ldr_quantize(const float* hdr, uint8_t* out, long long n_pixels, int mode, rfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,45 @@ static inline int grid_for(long long total) {
   return (int)(b < cap ? b : cap);
 }
 
+// ---------------------------------------------------------------------------------------------
+// HDR -> 8-bit LDR (the step right after the path: infer.py:94-98, batch_infer.py:153-157).
+// mode 0 ('none'): uint8(clip(x, 0, 1) * 255) -- the CLIs' default, reproduced bit-exactly (fp32
+//                  multiply, truncation like numpy's astype).
+// mode 1: Khronos PBR Neutral tone curve (published reference formula) followed by the sRGB OETF.
+//         The reference reaches it through simple_ocio / OpenColorIO, which is not vendored: unpinned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float srgb_oetf(float x) {
+  x = fminf(fmaxf(x, 0.f), 1.f);
+  return x <= 0.0031308f ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+}
+
+__global__ void ldr_quantize_kernel(const float* __restrict__ hdr, uint8_t* __restrict__ out, long long n_px,
+                                    int mode) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  float r = hdr[i * 3], g = hdr[i * 3 + 1], b = hdr[i * 3 + 2];
+  if (mode == 1) {
+    const float start = 0.8f - 0.04f, desat = 0.15f;
+    const float x = fminf(r, fminf(g, b));
+    const float off = x < 0.08f ? x - 6.25f * x * x : 0.04f;
+    r -= off, g -= off, b -= off;
+    const float peak = fmaxf(r, fmaxf(g, b));
+    if (peak >= start) {
+      const float d = 1.f - start;
+      const float np_ = 1.f - d * d / (peak + d - start);
+      const float sc = np_ / peak;
+      r *= sc, g *= sc, b *= sc;
+      const float t = 1.f - 1.f / (desat * (peak - np_) + 1.f);
+      r = r + (np_ - r) * t, g = g + (np_ - g) * t, b = b + (np_ - b) * t;
+    }
+    r = srgb_oetf(r), g = srgb_oetf(g), b = srgb_oetf(b);
+  }
+  // NaN clips to 0 like np.clip(...).astype(uint8) does for the CLIs' finite outputs; fp32 product, truncation
+  out[i * 3] = (uint8_t)(__fmul_rn(fminf(fmaxf(r, 0.f), 1.f), 255.f));
+  out[i * 3 + 1] = (uint8_t)(__fmul_rn(fminf(fmaxf(g, 0.f), 1.f), 255.f));
+  out[i * 3 + 2] = (uint8_t)(__fmul_rn(fminf(fmaxf(b, 0.f), 1.f), 255.f));
+}
+
 }  // namespace rfb
 
 using namespace rfb;
@@ -139,4 +178,11 @@ extern "C" int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, i
                                                                               Hi, Wi, Ho, Wo, C / 8);
   g_launch_count++;
   return check_launch("upsample_bilinear_kernel");
+}
+
+extern "C" int rfb_ldr_quantize(const float* hdr, uint8_t* out, long long n_pixels, int mode, rfb_stream_t stream) {
+  if (!hdr || !out || n_pixels <= 0 || (mode != 0 && mode != 1)) return RFB_ERR_ARG;
+  ldr_quantize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hdr, out, n_pixels, mode);
+  g_launch_count++;
+  return check_launch("ldr_quantize_kernel");
 }

@@ -209,8 +209,16 @@ class RenderFormerRenderingPipeline:
     def __call__(self, *args, **kwargs):
         return self.render(*args, **kwargs)
 
+    @staticmethod
+    def hdr_to_ldr(hdr: torch.Tensor, tone_mapper: str = "none") -> torch.Tensor:
+        """uint8 LDR image(s) from the HDR output, on the device: what infer.py:94-98 does with numpy
+        after the download ('none' = clip + truncate, bit-exact; 'pbr_neutral' = Khronos curve + sRGB)."""
+        from . import ops
+        return ops.ldr_quantize(hdr, tone_mapper)
+
     @torch.no_grad()
-    def render_stream(self, scenes, resolution: int = 512, torch_dtype: torch.dtype = torch.float16):
+    def render_stream(self, scenes, resolution: int = 512, torch_dtype: torch.dtype = torch.float16,
+                      ldr: Optional[str] = None):
         """Render a sequence of scenes given as HOST tensors (the batch_infer.py use case,
         batch_infer.py:103-143): generator over dicts with the keys of `render` ('triangles', 'texture',
         'mask', 'vn', 'c2w', 'fov'), yielding one pinned-host fp32 HDR tensor [B,V,H,W,3] per scene,
@@ -219,7 +227,9 @@ class RenderFormerRenderingPipeline:
         The host->device copy of scene i+1 (218 MB of texture for 4096 triangles) runs on a copy
         stream while scene i is being rendered, and the device->host copy of image i overlaps scene
         i+1; pass pinned tensors for truly asynchronous copies.  A yielded buffer belongs to a ring
-        of three and is overwritten two scenes later -- copy it if it must live longer."""
+        of three and is overwritten two scenes later -- copy it if it must live longer.
+        `ldr='none' | 'pbr_neutral'` tone-maps and quantises on the device and yields uint8 images
+        (a quarter of the download)."""
         dev = self.device
         if dev.type != "cuda":
             raise L.RfbError("render_stream needs a CUDA device (there is no CPU fallback)")
@@ -247,7 +257,9 @@ class RenderFormerRenderingPipeline:
                               resolution=resolution, torch_dtype=torch_dtype)
             for t in d.values():
                 t.record_stream(main)  # allocated on the copy stream, consumed on the main stream
-            if ring[slot] is None or ring[slot].shape != img.shape:
+            if ldr is not None:
+                img = self.hdr_to_ldr(img, ldr)
+            if ring[slot] is None or ring[slot].shape != img.shape or ring[slot].dtype != img.dtype:
                 ring[slot] = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
             host = ring[slot]
             slot = (slot + 1) % 3

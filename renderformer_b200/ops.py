@@ -223,3 +223,21 @@ def im2col_s2(x, out, *, B, H, W, C_):
 def upsample_bilinear(x, out, *, B, Hi, Wi, Ho, Wo, C_):
     L.check(_timed("upsample_bilinear", 0.0, lambda: L.load().rfb_upsample_bilinear(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C_, _stream())), "rfb_upsample_bilinear")
     return out
+
+
+TONE_MAPPERS = {"none": 0, "pbr_neutral": 1, "Khronos PBR Neutral": 1}
+
+
+def ldr_quantize(hdr: torch.Tensor, tone_mapper: str = "none") -> torch.Tensor:
+    """HDR fp32 [..., 3] -> uint8 [..., 3] on the device (infer.py:94-98).  'none' is the CLIs' default
+    clip-and-truncate, bit-exact; 'pbr_neutral' is the published Khronos curve + sRGB OETF (unpinned)."""
+    _need_cuda(hdr)
+    if tone_mapper not in TONE_MAPPERS:
+        raise ValueError(f"tone_mapper must be one of {sorted(TONE_MAPPERS)} (agx / filmic need OpenColorIO LUTs)")
+    if hdr.dtype != torch.float32 or hdr.shape[-1] != 3:
+        raise ValueError("hdr must be fp32 [..., 3]")
+    hdr = hdr.contiguous()
+    out = torch.empty(hdr.shape, dtype=torch.uint8, device=hdr.device)
+    L.check(_timed("ldr_quantize", 0.0, lambda: L.load().rfb_ldr_quantize(
+        hdr.data_ptr(), out.data_ptr(), hdr.numel() // 3, TONE_MAPPERS[tone_mapper], _stream())), "rfb_ldr_quantize")
+    return out

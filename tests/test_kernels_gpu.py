@@ -144,3 +144,29 @@ def test_cuda_graph_replay_matches_eager():
     assert len(pipe._graphs) == 2 and pipe.replayed_launches > 0
     for a, b in zip(graphed, eager + [eager[0]]):
         assert torch.equal(a, b)
+
+
+def test_ldr_quantize_bit_exact_and_streamed():
+    """Default LDR conversion of the CLIs, (np.clip(hdr, 0, 1) * 255).astype(uint8) (infer.py:97-98), is
+    reproduced bit-exactly on the device; the PBR-neutral curve is monotone and bounded."""
+    import numpy as np
+    from renderformer_b200.model import RenderFormerRenderingPipeline as P
+    g = torch.Generator().manual_seed(0)
+    hdr = torch.cat([torch.rand(5000, 3, generator=g) * 1.5 - 0.2, torch.rand(3000, 3, generator=g) * 50,
+                     torch.tensor([[0.0, 1.0, 0.5], [1 / 255, 2 / 255, 254.999 / 255], [1e-9, 0.99999994, 3.0]])])
+    hdr = hdr.view(1, 1, -1, 1, 3).contiguous()
+    want = (np.clip(hdr.numpy(), 0, 1) * 255).astype(np.uint8)
+    got = P.hdr_to_ldr(hdr.cuda(), "none").cpu().numpy()
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    ramp = torch.linspace(0, 8, 4096)[:, None].repeat(1, 3).contiguous().cuda()
+    pbr = P.hdr_to_ldr(ramp, "pbr_neutral").cpu().numpy().astype(int)
+    assert (np.diff(pbr[:, 0]) >= 0).all() and pbr.max() <= 255 and pbr[0, 0] == 0 and pbr[-1, 0] >= 250
+    with pytest.raises(ValueError):
+        P.hdr_to_ldr(ramp, "agx")
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, _ = _pipe(cfg, 9)
+    sc = make_scene(40, 2, seed=1)
+    g_ = {k: t.cuda() for k, t in sc.items()}
+    ref = pipe(g_["triangles"], g_["texture"], g_["mask"], g_["vn"], g_["c2w"], g_["fov"], resolution=64).cpu().numpy()
+    out = [x.clone() for x in pipe.render_stream(iter([sc]), resolution=64, ldr="none")]
+    assert out[0].dtype == torch.uint8 and np.array_equal(out[0].numpy(), (np.clip(ref, 0, 1) * 255).astype(np.uint8))
