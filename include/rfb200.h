@@ -195,6 +195,10 @@ int rfb_vn_encode(const float* vn, void* out, int n, int nfreq, int ld, rfb_stre
  * models/view_transformer.py:104-107); fov in degrees. */
 int rfb_ray_tokens(const float* fov_deg, void* out, int n_views, int resolution, rfb_stream_t stream);
 
+/* explicit ray map fp32 [V, R, R, 3] -> patch tokens f16 [V, (R/8)^2, 192] (models/view_transformer.py:104-107):
+ * the model-level entry RenderFormer.forward(..., rays_d, tri_vpos_view_tf) hands rays in instead of cameras. */
+int rfb_ray_map_tokens(const float* rays_d, void* out, int n_views, int resolution, rfb_stream_t stream);
+
 /* RoPE positions [V, rows_out, 9]: register rows = masked centroid, then T_v^-1 * triangle
  * (models/renderformer.py:103-124, utils/transform.py:7-27).  c2w NULL = world space. */
 int rfb_positions(const float* tri, const uint8_t* mask, const float* c2w, float* pos, int n, int n_reg,

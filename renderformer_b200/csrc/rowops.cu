@@ -387,6 +387,22 @@ __global__ void ray_tokens_kernel(const float* __restrict__ fov_deg, uint16_t* _
   out[t] = *reinterpret_cast<uint16_t*>(&h);
 }
 
+// explicit ray map [V, R, R, 3] fp32 -> patch tokens (same layout as ray_tokens_kernel): the model-level
+// entry RenderFormer.forward(..., rays_d, ...) (models/renderformer.py:171-206) hands the rays in
+__global__ void ray_map_tokens_kernel(const float* __restrict__ rays, uint16_t* __restrict__ out, int V, int R) {
+  const int P = 8, T = R / P;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_view = (long long)T * T * 192;
+  if (t >= V * per_view) return;
+  const int v = t / per_view;
+  const int rem = t % per_view;
+  const int tok = rem / 192, f = rem % 192;
+  const int c = f >> 6, p1 = (f >> 3) & 7, p2 = f & 7;
+  const int py = (tok / T) * P + p1, px = (tok % T) * P + p2;
+  __half h = __float2half(rays[(((long long)v * R + py) * R + px) * 3 + c]);
+  out[t] = *reinterpret_cast<uint16_t*>(&h);
+}
+
 // RoPE positions: pos[v, 0:n_reg] = masked vertex centroid (x3), pos[v, n_reg + i] = T_v^-1 tri_i.
 //   models/renderformer.py:103-124, utils/transform.py:7-27.  One block per view; c2w == NULL
 //   keeps world coordinates (the view-independent stage).
@@ -561,6 +577,14 @@ extern "C" int rfb_ray_tokens(const float* fov_deg, void* out, int n_views, int 
   ray_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fov_deg, (uint16_t*)out,
                                                                                        n_views, resolution);
   RFB_LAUNCHED("ray_tokens_kernel");
+}
+
+extern "C" int rfb_ray_map_tokens(const float* rays_d, void* out, int n_views, int resolution, rfb_stream_t stream) {
+  if (!rays_d || !out || n_views <= 0 || resolution % 8) return RFB_ERR_ARG;
+  const long long total = (long long)n_views * (resolution / 8) * (resolution / 8) * 192;
+  ray_map_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_d, (uint16_t*)out,
+                                                                                           n_views, resolution);
+  RFB_LAUNCHED("ray_map_tokens_kernel");
 }
 
 extern "C" int rfb_positions(const float* tri, const uint8_t* mask, const float* c2w, float* pos, int n,

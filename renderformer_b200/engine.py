@@ -325,11 +325,18 @@ class Engine:
         return self._maps[key]
 
     @torch.no_grad()
-    def render_views(self, st: SceneState, b: int, c2w: torch.Tensor, fov_deg: torch.Tensor, resolution: int,
-                     taps: Optional[dict] = None) -> torch.Tensor:
-        """Render V views of scene `b`.  c2w [V,4,4], fov_deg [V] or [V,1] -> HDR fp32 [V,R,R,3]."""
+    def render_views(self, st: SceneState, b: int, c2w: Optional[torch.Tensor], fov_deg: Optional[torch.Tensor],
+                     resolution: int, taps: Optional[dict] = None, rays_d: Optional[torch.Tensor] = None,
+                     tri_cam: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Render V views of scene `b` -> HDR fp32 [V,R,R,3].  Either cameras (c2w [V,4,4], fov_deg [V] or
+        [V,1]; rays and camera-space triangles are derived on the device) or, for the model-level entry
+        (models/renderformer.py:171-206), an explicit camera-space ray map `rays_d` [V,R,R,3] together
+        with the camera-space triangles `tri_cam` [V,N,9]."""
         cfg, w, dev = self.cfg, self.w, self.device
-        V, R = c2w.shape[0], resolution
+        explicit = rays_d is not None
+        if explicit and tri_cam is None:
+            raise ValueError("rays_d needs tri_cam (camera-space triangle vertices)")
+        V, R = (rays_d.shape[0] if explicit else c2w.shape[0]), resolution
         if R % 64 != 0 and cfg.view_transformer_use_swin_attn:
             raise ValueError("resolution must be a multiple of 64 for swin attention")  # SURVEY §8b
         if R % 8 != 0:
@@ -340,12 +347,20 @@ class Engine:
         Ntp, N = st.Ntp, st.N
         rows = V * Nr
         bf = torch.bfloat16
-        c2w = c2w.to(dev, torch.float32).contiguous()
-        fov = fov_deg.reshape(-1).to(dev, torch.float32).contiguous()
-
-        pos = ops.positions(st.tri[b], st.mask_u8[b], c2w, self._e((V, Ntp, 9), torch.float32), n=N,
-                            n_reg=cfg.num_register_tokens, rows_out=Ntp, n_views=V)
-        rt = ops.ray_tokens(fov, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
+        if explicit:
+            rays = rays_d.to(dev, torch.float32).contiguous()
+            tc = tri_cam.reshape(V, N, 9).to(dev, torch.float32).contiguous()
+            pos = self._e((V, Ntp, 9), torch.float32)
+            for vi in range(V):  # centroid registers + vertices, already in camera space
+                ops.positions(tc[vi], st.mask_u8[b], None, pos[vi], n=N, n_reg=cfg.num_register_tokens, rows_out=Ntp,
+                              n_views=1)
+            rt = ops.ray_map_tokens(rays, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
+        else:
+            c2w = c2w.to(dev, torch.float32).contiguous()
+            fov = fov_deg.reshape(-1).to(dev, torch.float32).contiguous()
+            pos = ops.positions(st.tri[b], st.mask_u8[b], c2w, self._e((V, Ntp, 9), torch.float32), n=N,
+                                n_reg=cfg.num_register_tokens, rows_out=Ntp, n_views=V)
+            rt = ops.ray_tokens(fov, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
         lin = ops.gemm(rt, w["ray.w"], bias=w["ray.b"], out_dtype=torch.float32)
         x = self._e((rows, dv), torch.float32)
         ops.token_assemble(lin, w["ray.norm"], None, None, w["ray.token"], None, x, n_prefix=0, rows_in=rows,

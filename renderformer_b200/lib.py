@@ -65,7 +65,7 @@ class AttnArgs(C.Structure):
 # every symbol include/rfb200.h declares (tests/test_abi.py checks the built library exports them)
 SYMBOLS = [
     "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope",
-    "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_positions",
+    "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_ray_map_tokens", "rfb_positions",
     "rfb_pack_mask", "rfb_cast", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear", "rfb_ldr_quantize",
 ]
 
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
         "rfb_texture_prep": [p, p, ll, i, i, i, p],
         "rfb_texture_const_prep": [p, p, ll, i, i, i, p],
         "rfb_ldr_quantize": [p, p, ll, i, p],
+        "rfb_ray_map_tokens": [p, p, i, i, p],
         "rfb_vn_encode": [p, p, i, i, i, p],
         "rfb_ray_tokens": [p, p, i, i, p],
         "rfb_positions": [p, p, p, p, i, i, i, i, p],

@@ -91,18 +91,26 @@ class RenderFormer(_Params):
     @torch.no_grad()
     def forward(self, tri_vpos_list, texture_patch_list, valid_mask, vns, rays_o=None, rays_d=None,
                 tri_vpos_view_tf=None, tf32_view_tf: bool = False, *, c2w=None, fov=None, resolution=None):
-        """Reference signature (models/renderformer.py:171-206).  The view stage needs the cameras:
-        pass `c2w` [B,V,4,4], `fov` [B,V,1] (degrees) and `resolution` -- the ray map and the
-        camera-space triangles are then rebuilt on the device, so `rays_o`, `rays_d` and
-        `tri_vpos_view_tf` may be None.  Returns log-encoded images [B, V, 3, H, W] like the
-        reference; the pipeline calls the engine directly and skips this round trip."""
-        if c2w is None or fov is None or resolution is None:
-            raise NotImplementedError("RenderFormer.forward needs c2w/fov/resolution keyword arguments; "
-                                      "use RenderFormerRenderingPipeline.render for the reference call surface")
+        """Reference signature and semantics (models/renderformer.py:171-206): tri_vpos_list [B,N,9],
+        texture_patch_list [B,N,13,P,P] with the emission channels ALREADY log-encoded (the pipeline does
+        that before calling the model, rendering_pipeline.py:67-68), valid_mask [B,N], vns [B,N,9],
+        rays_o [B,V,3] (unused: the origin is 0 in camera space), rays_d [B,V,H,W,3] camera-space ray
+        map, tri_vpos_view_tf [B,V,N,9] camera-space vertices.  Returns log-encoded images
+        [B, V, 3, H, W] like the reference.  Alternatively pass cameras as keywords (`c2w` [B,V,4,4],
+        `fov` [B,V,1] degrees, `resolution`) and leave rays_d / tri_vpos_view_tf None.  The pipeline
+        calls the engine directly and skips the log round trip."""
         eng = self.engine()
-        B = c2w.shape[0]
         st = eng.encode_scene(tri_vpos_list, texture_patch_list, valid_mask, vns, texture_is_log=True)
-        out = [eng.render_views(st, b, c2w[b], fov[b], resolution) for b in range(B)]
+        if rays_d is not None and tri_vpos_view_tf is not None:
+            B, V, R = rays_d.shape[0], rays_d.shape[1], rays_d.shape[2]
+            assert rays_d.shape[3] == R, "square images only"
+            out = [eng.render_views(st, b, None, None, R, rays_d=rays_d[b], tri_cam=tri_vpos_view_tf[b])
+                   for b in range(B)]
+        elif c2w is not None and fov is not None and resolution is not None:
+            out = [eng.render_views(st, b, c2w[b], fov[b], resolution) for b in range(c2w.shape[0])]
+        else:
+            raise ValueError("RenderFormer.forward needs either rays_d + tri_vpos_view_tf (reference signature) "
+                             "or the c2w / fov / resolution keywords")
         hdr = torch.stack(out, dim=0)  # [B,V,H,W,3]
         return torch.log10(hdr + 1.0).permute(0, 1, 4, 2, 3)
 

@@ -191,6 +191,13 @@ def ray_tokens(fov_deg, out, *, n_views, resolution):
     return out
 
 
+def ray_map_tokens(rays_d, out, *, n_views, resolution):
+    _need_cuda(rays_d, out)
+    L.check(_timed("ray_map_tokens", 0.0, lambda: L.load().rfb_ray_map_tokens(rays_d.data_ptr(), out.data_ptr(), n_views,
+                                                                              resolution, _stream())), "rfb_ray_map_tokens")
+    return out
+
+
 def positions(tri, mask_u8, c2w, pos, *, n, n_reg, rows_out, n_views):
     _need_cuda(tri, mask_u8, pos)
     L.check(_timed("positions", 0.0, lambda: L.load().rfb_positions(tri.data_ptr(), mask_u8.data_ptr(), _p(c2w), pos.data_ptr(), n, n_reg, rows_out,

@@ -170,3 +170,34 @@ def test_ldr_quantize_bit_exact_and_streamed():
     ref = pipe(g_["triangles"], g_["texture"], g_["mask"], g_["vn"], g_["c2w"], g_["fov"], resolution=64).cpu().numpy()
     out = [x.clone() for x in pipe.render_stream(iter([sc]), resolution=64, ldr="none")]
     assert out[0].dtype == torch.uint8 and np.array_equal(out[0].numpy(), (np.clip(ref, 0, 1) * 255).astype(np.uint8))
+
+
+def test_model_forward_reference_signature():
+    """RenderFormer.forward with the reference's own arguments (models/renderformer.py:171-206): log-encoded
+    texture, explicit camera-space ray map and camera-space triangles, log-encoded [B,V,3,H,W] output --
+    checked against the oracle's scene_stage / view_stage and against the pipeline's camera path."""
+    import math
+
+    from oracle import renderformer_oracle as orc
+    from renderformer_b200.model import RenderFormer
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, sd = _pipe(cfg, 21)
+    model: RenderFormer = pipe.model
+    sc = make_scene(60, 2, seed=6, pad_to=64)
+    B, V, N, R = 1, 2, 64, 64
+    tex_log = sc["texture"].clone()
+    tex_log[:, :, -3:] = torch.log10(tex_log[:, :, -3:] + 1.0)
+    tri_cam = orc.to_camera_space(sc["c2w"][0], sc["triangles"].expand(V, -1, -1, -1)).reshape(1, V, N, 9)
+    rays = orc.camera_rays(sc["fov"][0] / 180.0 * math.pi, R)[None]  # [1,V,R,R,3]
+    out = model(sc["triangles"].reshape(B, N, 9).cuda(), tex_log.cuda(), sc["mask"].cuda(),
+                sc["vn"].reshape(B, N, 9).cuda(), rays_o=torch.zeros(B, V, 3).cuda(), rays_d=rays.cuda(),
+                tri_vpos_view_tf=tri_cam.cuda(), tf32_view_tf=True)
+    assert out.shape == (B, V, 3, R, R)
+    hdr = (torch.pow(10.0, out) - 1.0).permute(0, 1, 3, 4, 2).cpu()
+    ref = orc.render(sd, cfg, sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], R)
+    rel, psnr = hdr_rel_err(hdr, ref), log_psnr(hdr, ref)
+    print(f"model.forward (reference signature) vs oracle: hdr rel {rel:.3e} log-PSNR {psnr:.1f} dB")
+    assert rel <= REL_TOL and psnr >= PSNR_MIN
+    g = {k: v.cuda() for k, v in sc.items()}
+    cam = pipe(g["triangles"], g["texture"], g["mask"], g["vn"], g["c2w"], g["fov"], resolution=R).cpu()
+    assert hdr_rel_err(hdr, cam) < 3e-3  # same kernels; rays / transforms computed on the host here
