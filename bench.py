@@ -215,7 +215,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    graphs = world == 1 and not args.no_cuda_graphs
+    graphs = not args.no_cuda_graphs
+    recv_state = None
 
     def step_device(inp):
         """Both stages with inputs resident in HBM; returns this rank's images."""
@@ -225,8 +226,10 @@ def main():
                                    inp["fov_local"], resolution=R, torch_dtype=torch.bfloat16)
             st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"])
         else:
-            st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"]) if rank == 0 \
-                else eng.alloc_scene_state(1, N)
+            nonlocal recv_state
+            if rank != 0 and recv_state is None:
+                recv_state = pipe.static_scene_state(1, N)  # persistent receive buffers
+            st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"]) if rank == 0 else recv_state
             broadcast_scene_state(st, src=0)  # per-layer triangle K/V + tokens over NVLink (NCCL)
         img = pipe.render_views(st, inp["c2w_local"], inp["fov_local"], R)
         if world > 1:
@@ -391,7 +394,8 @@ def main():
                             f"{Vl} views/GPU per step ({frames} views total; 32-view batch at 8 GPUs = BASELINE configs[2]); "
                             "scene stage once per step on rank 0 + NCCL broadcast of per-layer K/V",
                 "l2": "inputs + weights (~1.3 GB per step) exceed the 126 MB L2; no explicit flush",
-                "launch": ("one CUDA-graph replay per step (pipeline.cuda_graphs)" if graphs else "eager launches from Python"),
+                "launch": (("one CUDA-graph replay per step" if world == 1 else "CUDA-graph replay of each stage, NCCL eager")
+                           + " (pipeline.cuda_graphs)" if graphs else "eager launches from Python"),
                 "algorithmic_tflop_per_step": step_tflop,
                 "model_flops_utilisation": step_tflop / (ms_step * 1e-3) / world / load_peaks()[0],
                 "scene_tflop": scene_flops(cfg, N) / 1e12, "view_tflop": view_flops(cfg, N, R) / 1e12,

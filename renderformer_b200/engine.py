@@ -45,6 +45,7 @@ class SceneState:
     v_all: torch.Tensor      # bf16 [B, L*dv, Ntp]: hoisted decoder V of every layer, transposed
 
     dv: int = 0              # decoder width (columns of one layer inside k_all / rows inside v_all)
+    static: bool = False     # buffers persist across calls (CUDA-graph output / broadcast receive buffer)
 
     def k_pre(self, layer: int, b: int) -> torch.Tensor:
         """fp32 [Ntp, dv] view (row stride L*dv)."""

@@ -148,12 +148,24 @@ class RenderFormerRenderingPipeline:
 
     @torch.no_grad()
     def encode(self, triangles, texture, mask, vn) -> SceneState:
-        """View-independent stage only (exposed for multi-GPU view sharding)."""
-        return self.model.engine().encode_scene(triangles, texture, mask, vn)
+        """View-independent stage only (exposed for multi-GPU view sharding).  With `cuda_graphs` the
+        returned SceneState is the graph's static output (overwritten by the next call of that shape)."""
+        eng = self.model.engine()
+        inputs = (triangles, texture, mask, vn)
+        if self.cuda_graphs and all(t.is_cuda for t in inputs):
+            st = self._graph_entry(("encode", id(eng)) + self._sig(inputs), inputs,
+                                   lambda a, b, c, d: eng.encode_scene(a, b, c, d))
+            st.static = True
+            return st
+        return eng.encode_scene(triangles, texture, mask, vn)
 
     @torch.no_grad()
-    def render_views(self, state: SceneState, c2w, fov, resolution: int = 512) -> torch.Tensor:
+    def render_views(self, state: SceneState, c2w, fov, resolution: int = 512, _eager: bool = False) -> torch.Tensor:
         eng = self.model.engine()
+        if self.cuda_graphs and not _eager and getattr(state, "static", False) and c2w.is_cuda and fov.is_cuda:
+            # the graph reads the persistent state in place (no copy of the 300 MB of hoisted K / V)
+            return self._graph_entry(("views", id(eng), id(state), resolution, self.view_chunk) + self._sig((c2w, fov)),
+                                     (c2w, fov), lambda a, b: self.render_views(state, a, b, resolution, _eager=True))
         B, V = c2w.shape[:2]
         out = []
         for b in range(B):
@@ -184,28 +196,24 @@ class RenderFormerRenderingPipeline:
         state = self.encode(triangles, texture, mask, vn)
         return self.render_views(state, c2w, fov, resolution)
 
-    def _render_graphed(self, inputs, resolution: int) -> torch.Tensor:
-        eng = self.model.engine()
-        key = (id(eng), resolution, self.view_chunk) + tuple((tuple(t.shape), t.dtype) for t in inputs)
+    def _graph_entry(self, key, inputs, fn):
+        """Capture `fn(*static_inputs)` once per key, replay it with `inputs` copied into the static
+        buffers; returns the graph's static result."""
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) >= self.max_cached_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
             static_in = [t.detach().clone().contiguous() for t in inputs]
-
-            def run():
-                st = eng.encode_scene(static_in[0], static_in[1], static_in[2], static_in[3])
-                return self.render_views(st, static_in[4], static_in[5], resolution)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):  # warm-up outside the capture: lazy attribute set-up, maps, allocator
                 for _ in range(2):
-                    run()
+                    fn(*static_in)
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(graph):
-                static_out = run()
+                static_out = fn(*static_in)
             entry = self._graphs[key] = (graph, static_in, static_out, L.launch_count() - n0)
         graph, static_in, static_out, n_kernels = entry
         for dst, src in zip(static_in, inputs):
@@ -213,6 +221,24 @@ class RenderFormerRenderingPipeline:
         graph.replay()
         self.replayed_launches += n_kernels
         return static_out
+
+    @staticmethod
+    def _sig(tensors):
+        return tuple((tuple(t.shape), t.dtype) for t in tensors)
+
+    def _render_graphed(self, inputs, resolution: int) -> torch.Tensor:
+        eng = self.model.engine()
+
+        def run(tri, tex, mask, vn, c2w, fov):
+            return self.render_views(eng.encode_scene(tri, tex, mask, vn), c2w, fov, resolution, _eager=True)
+        return self._graph_entry(("render", id(eng), resolution, self.view_chunk) + self._sig(inputs), inputs, run)
+
+    def static_scene_state(self, B: int, N: int) -> SceneState:
+        """A persistent SceneState (receive buffer of the NCCL broadcast on ranks that do not encode);
+        `render_views` on it is replayed from a CUDA graph when `cuda_graphs` is on."""
+        st = self.model.engine().alloc_scene_state(B, N)
+        st.static = True
+        return st
 
     def __call__(self, *args, **kwargs):
         return self.render(*args, **kwargs)
