@@ -98,6 +98,17 @@ typedef struct {
   long long ld16;
   const float* col_mul;   /* [N] or NULL */
   const int* aux_row_map; /* row of out16 / out_sumsq = aux_row_map ? aux_row_map[out_row] : out_row */
+  /* ---- transposed side output (RFB_EPI_STORE, linear A): the V part of a fused [q | k | v] projection.
+   * Columns n >= vt_split are not written to out / out16 but, multiplied by the row factor r, to
+   * vt_out[b][n - vt_split][m - b*vt_rows_per_batch] (16-bit), b = m / vt_rows_per_batch (0 if that is 0):
+   * V arrives transposed (keys contiguous) as rfb_attention wants it, without a second GEMM.
+   * vt_split must be a multiple of 256 (a whole number of N tiles). */
+  void* vt_out;
+  int vt_dtype;
+  int vt_split;
+  int vt_rows_per_batch;
+  long long vt_ld;
+  long long vt_batch_stride;
 } rfb_gemm_args;
 
 int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream);

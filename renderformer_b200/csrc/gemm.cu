@@ -57,6 +57,10 @@ struct GemmKParams {
   long long ld16;
   const float* col_mul;
   const int* aux_row_map;
+  // transposed side output: columns n >= vt_split go to vt_out[b][n - vt_split][row] (16-bit, x r)
+  void* vt_out;
+  int vt_dtype, vt_split, vt_rows_per_batch;
+  long long vt_ld, vt_batch_stride;
 };
 
 constexpr int kBM = 128;
@@ -413,6 +417,44 @@ __device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Transposed tile: the V part of a fused [q | k | v] projection.  A thread owns one row (token) and
+// 32 consecutive columns (feature dims); for a fixed column the warp's 32 lanes hold 32 consecutive
+// tokens, so each column is one 64-byte store into V^T[dim][token] -- no staging needed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_vt_chunks(const GemmKParams& p, uint32_t taddr0, int n0, int c_begin,
+                                                   int c_end, int m, bool valid, float rs, uint64_t* tfull_bar,
+                                                   uint32_t parity) {
+  mbar_wait(tfull_bar, parity);
+  tc_fence_after();
+  const int b = p.vt_rows_per_batch > 0 ? m / p.vt_rows_per_batch : 0;
+  const int mrow = m - b * p.vt_rows_per_batch;
+  uint16_t* base = static_cast<uint16_t*>(p.vt_out) + (long long)b * p.vt_batch_stride + mrow;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    if (n0 + c * 32 >= p.N) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(taddr0 + c * 32, v);
+    tmem_wait_ld();
+    if (valid) {
+      uint16_t* col = base + (long long)(n0 + c * 32 - p.vt_split) * p.vt_ld;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (n0 + c * 32 + i < p.N) {
+          const float x = __uint_as_float(v[i]) * rs;
+          uint16_t h;
+          if (p.vt_dtype == RFB_BF16) {
+            h = static_cast<uint16_t>(pack_bf16(x, 0.f) & 0xffffu);
+          } else {
+            h = static_cast<uint16_t>(pack_f16(x, 0.f) & 0xffffu);
+          }
+          col[(long long)i * p.vt_ld] = h;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Specialised epilogue of one warp's half tile (4 chunks of 32 columns, BN == 256, N % 256 == 0)
 // for EK_RESID / EK_PROJ16.  Everything that is constant over the tile's chunks (output rows,
 // 1/rms, smem addresses) lives in registers, the chunk loop is fully unrolled so the residual
@@ -672,7 +714,10 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
       constexpr int HALF = (NCH + 1) / 2;
       const int c_begin = ((warp - EPI0) >> 2) * HALF;
       const int c_end = (c_begin + HALF < NCH) ? c_begin + HALF : NCH;
-      if constexpr (EK != EK_GENERIC) {
+      if (p.vt_out && n0 >= p.vt_split) {  // tile of the transposed (V) part: warp-uniform per tile
+        epilogue_vt_chunks(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, n0, c_begin, c_end,
+                           mt * kBM + r, valid, rs, &tfull[as], aph);
+      } else if constexpr (EK != EK_GENERIC) {
         static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
         epilogue_half_tile_fast<EK>(p, my_stage, lane,
                                     tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
@@ -760,6 +805,14 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   p.out_sumsq = a->out_sumsq, p.out_sumsq_ld = a->out_sumsq_ld;
   p.out16 = a->out16, p.out16_dtype = a->out16_dtype, p.ld16 = a->ld16;
   p.col_mul = a->col_mul, p.aux_row_map = a->aux_row_map;
+  p.vt_out = a->vt_out, p.vt_dtype = a->vt_dtype, p.vt_split = a->vt_split;
+  p.vt_rows_per_batch = a->vt_rows_per_batch, p.vt_ld = a->vt_ld, p.vt_batch_stride = a->vt_batch_stride;
+  if (a->vt_out) {
+    if (a->a_mode != RFB_A_LINEAR || a->epi != RFB_EPI_STORE || a->row_map || a->vt_split <= 0 || a->vt_split >= a->N ||
+        a->vt_split % 256 || (a->vt_dtype != RFB_BF16 && a->vt_dtype != RFB_F16) || a->vt_ld < 1 ||
+        (a->in_rscale && a->scale_dim == 1))
+      return RFB_ERR_ARG;
+  }
   const bool fused_any = a->in_sumsq || a->in_rscale || a->out_rscale || a->out_sumsq || a->out16 || a->col_mul;
   if (a->in_sumsq && (a->norm_dim <= 0 || a->in_rscale || p.in_sumsq_parts > p.in_sumsq_ld)) return RFB_ERR_ARG;
   if (a->in_rscale && a->scale_dim != 0 && a->scale_dim != 1) return RFB_ERR_ARG;
@@ -770,10 +823,15 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     return RFB_ERR_ARG;
   if (a->out16 && (a->ld16 % 8 || (a->out16_dtype != RFB_BF16 && a->out16_dtype != RFB_F16))) return RFB_ERR_ARG;
   if (a->out16 && a->N % 8) return RFB_ERR_ARG;
-  if (a->out_sumsq && (a->N % 128 || a->out_sumsq_ld < a->N / 128)) return RFB_ERR_ARG;
+  const int n_plain = a->vt_out ? a->vt_split : a->N;  // columns that go through the ordinary epilogue
+  if (a->out_sumsq && (n_plain % 128 || a->out_sumsq_ld < n_plain / 128)) return RFB_ERR_ARG;
   if (a->res2 && (a->res_dtype == RFB_F32 || !a->res1)) return RFB_ERR_ARG;
 
   int bn = a->bn_override;
+  if (a->vt_out) {
+    if (bn != 0 && bn != 256) return RFB_ERR_ARG;
+    bn = 256;  // vt_split is a whole number of 256-wide tiles
+  }
   if (a->out_sumsq) {
     if (bn != 0 && bn != 256) return RFB_ERR_ARG;
     bn = 256;  // one epilogue warp per 128-column sum-of-squares part
@@ -789,7 +847,7 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RFB_ERR_ARG;
 
   if (a->epi == RFB_EPI_STORE) {
-    p.n_store = (a->N + 7) & ~7;
+    p.n_store = (n_plain + 7) & ~7;
     if (p.n_store > a->ldo) return RFB_ERR_ARG;
     if ((a->bias || a->res1 || a->res2) && (a->N % 8) != 0) return RFB_ERR_ARG;
     if (!a->out && !a->out_act && !a->out16) return RFB_ERR_ARG;

@@ -294,6 +294,69 @@ static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool
   if (scale_dim == 0) report((nm + " [rscale]").c_str(), drs.down(), hscale, 1e-5, 1e-4, 1);
 }
 
+// fused [q | k | v] projection: columns >= split leave transposed (V^T[b][dim][token]) times the row factor
+static void run_vt(const char* name, int M, int N, int K, int split, int rows_per_batch, bool proj16) {
+  std::vector<uint16_t> hA = rand16((size_t)M * K, 15, 1.0f, RFB_BF16), hW = rand16((size_t)N * K, 16, 0.05f, RFB_BF16);
+  DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K);
+  dA.up(hA), dW.up(hW);
+  DevBuf<float> dacc((size_t)M * N);
+  dim3 g((N + 127) / 128, M);
+  ref_linear<<<g, 128>>>(dA.p, K, dW.p, K, dacc.p, M, N, K, 1);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> acc = dacc.down();
+  const float eps = 1e-6f;
+  const int norm_dim = 512, parts = 4;
+  std::vector<float> hparts((size_t)M * parts), hrs(M), hcm = rand32(split, 10, 1.0f);
+  for (int m = 0; m < M; ++m) {
+    float tot = 0.f;
+    for (int j = 0; j < parts; ++j) tot += (hparts[(size_t)m * parts + j] = 50.f + 100.f * (0.5f + 0.5f * hval(29, m * 4 + j)));
+    hrs[m] = 1.0f / sqrtf(tot / norm_dim + eps);
+  }
+  DevBuf<float> dparts(hparts.size()), dcm(split);
+  dparts.up(hparts), dcm.up(hcm);
+  const int nb = rows_per_batch > 0 ? M / rows_per_batch : 1;
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : M;
+  const int nv = N - split;
+  const long long vt_ld = (rpb + 7) & ~7;
+  DevBuf<uint16_t> dvt((size_t)nb * nv * vt_ld), do16((size_t)M * split);
+  DevBuf<float> dout((size_t)M * split), dosq((size_t)M * (split / 128));
+  dvt.fill_byte(0), do16.fill_byte(0), dout.fill_byte(0), dosq.fill_byte(0x7f);
+  rfb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = K, a.W = dW.p, a.ldw = K, a.dtype = RFB_BF16, a.epi = RFB_EPI_STORE;
+  a.in_sumsq = dparts.p, a.in_sumsq_ld = parts, a.in_sumsq_parts = parts, a.norm_dim = norm_dim, a.norm_eps = eps;
+  a.out_dtype = RFB_F32, a.ldo = split;
+  if (proj16) {
+    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = split, a.col_mul = dcm.p;
+    a.out_sumsq = dosq.p, a.out_sumsq_ld = split / 128;
+  } else {
+    a.out = dout.p;
+  }
+  a.vt_out = dvt.p, a.vt_dtype = RFB_BF16, a.vt_split = split, a.vt_rows_per_batch = rows_per_batch, a.vt_ld = vt_ld;
+  a.vt_batch_stride = (long long)nv * vt_ld;
+  int rc = rfb_gemm(&a, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc != RFB_OK || e != cudaSuccess) {
+    printf("[FAIL] %-46s rc=%d cuda=%s\n", name, rc, cudaGetErrorString(e));
+    g_fail++;
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  std::vector<float> exp((size_t)M * split), exp16((size_t)M * split), expvt((size_t)nb * nv * vt_ld, 0.f);
+  for (int m = 0; m < M; ++m) {
+    for (int n = 0; n < split; ++n) {
+      exp[(size_t)m * split + n] = acc[(size_t)m * N + n] * hrs[m];
+      exp16[(size_t)m * split + n] = exp[(size_t)m * split + n] * hcm[n];
+    }
+    const int b = m / rpb, mr = m % rpb;
+    for (int n = split; n < N; ++n) expvt[((size_t)b * nv + (n - split)) * vt_ld + mr] = acc[(size_t)m * N + n] * hrs[m];
+  }
+  std::string nm(name);
+  if (proj16) report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * split, RFB_BF16), exp16, 2e-2, 1.2e-2, split);
+  else report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, split);
+  report((nm + " [v^T]").c_str(), to_float(dvt.p, expvt.size(), RFB_BF16), expvt, 2e-2, 1.2e-2, (int)vt_ld);
+}
+
 // micro-benchmark of the fused residual / projection epilogues at the decoder's shapes
 static void bench_fused(const char* name, int M, int N, int K, bool res, bool sumsq, bool o16, bool in_sq, bool maps,
                         bool f32out) {
@@ -423,6 +486,9 @@ int main(int argc, char** argv) {
       run_fused("EK_RESID 1031x1024x512 res", 1031, 1024, 512, 0, false, false, true, false, 1);
       run_fused("EK_RESID 1031x512x256 res rowmap auxmap", 1031, 512, 256, 0, false, true, true, true, 1);
       run_fused("EK_PROJ16 1031x2048x256", 1031, 2048, 256, 0, false, false, false, false, 2);
+      run_vt("fused qkv (generic) 517x768x256 split 512", 517, 768, 256, 512, 0, false);
+      run_vt("fused qkv (generic) 2x264 rows, batched v^T", 528, 768, 256, 512, 264, false);
+      run_vt("fused qkv (PROJ16) 1031x1536x256 split 1024", 1031, 1536, 256, 1024, 0, true);
       run_fused("fused swiglu rowscale 777x2048x512", 777, 2048, 512, 0, true, false, false);
     }
     printf("selftest_gemm: %d failure(s)\n", g_fail);

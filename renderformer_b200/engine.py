@@ -144,7 +144,7 @@ class Engine:
         for i in range(cfg.num_layers):
             p, o = f"transformer.layers.{i}.", f"enc{i}."
             w_in = fold(g(p + "multihead_attn.in_proj.weight"), p + "query_norm.weight")
-            put(o + "wqk", w_in[: 2 * d], bf), put(o + "wv", w_in[2 * d:], bf)
+            put(o + "wqkv", w_in, bf)  # one GEMM: q | k to fp32, v transposed (vt_out)
             put(o + "wo", g(p + "multihead_attn.out_proj.weight"), bf)
             put(o + "qkn", torch.cat([g(p + "multihead_attn.q_norm.weight"), g(p + "multihead_attn.k_norm.weight")]))
             put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight"), bf)
@@ -165,7 +165,10 @@ class Engine:
             put(o + "qn", g(p + "multihead_attn.q_norm.weight")), put(o + "kn", g(p + "multihead_attn.k_norm.weight"))
             put(o + "n_q", g(p + "query_norm.weight"))
             w_in = fold(g(p + "self_attn.in_proj.weight"), p + "self_attn_norm.weight", fused_dec)
-            put(o + "s.wqk", w_in[: 2 * dv], bf), put(o + "s.wv", w_in[2 * dv:], bf)
+            if fused_dec:
+                put(o + "s.wqkv", w_in, bf)
+            else:
+                put(o + "s.wqk", w_in[: 2 * dv], bf), put(o + "s.wv", w_in[2 * dv:], bf)
             put(o + "s.wo", g(p + "self_attn.out_proj.weight"), bf)
             put(o + "s.qkn", torch.cat([g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight")]))
             put(o + "n_s", g(p + "self_attn_norm.weight")), put(o + "n_f", g(p + "ffn_norm.weight"))
@@ -174,8 +177,8 @@ class Engine:
 
         Lv = cfg.view_transformer_n_layers
         put("dec.kn_all", torch.cat([self.w.pop(f"dec{i}.kn") for i in range(Lv)], dim=0))
-        put("dec.wk_all", torch.cat([self.w.pop(f"dec{i}.wk") for i in range(Lv)], dim=0))
-        put("dec.wv_all", torch.cat([self.w.pop(f"dec{i}.wv") for i in range(Lv)], dim=0))
+        put("dec.wkv_all", torch.cat([self.w.pop(f"dec{i}.wk") for i in range(Lv)] +
+                                     [self.w.pop(f"dec{i}.wv") for i in range(Lv)], dim=0))
 
         h = v + "out_dpt."
         for i in range(4):
@@ -262,15 +265,12 @@ class Engine:
         P = d // 128
         xb, xsq = self._e((rows, d), bf), self._e((rows, P), f32)
         xb2, xsq2 = self._e((rows, d), bf), self._e((rows, P), f32)
-        rsc = self._e((rows,), f32)
         ops.rowstat(x, xb, xsq, rows=rows, d=d)
         for i in range(cfg.num_layers):
             o = f"enc{i}."
-            qk = ops.gemm(xb, w[o + "wqk"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc, **nrm)
             vt = self._e((B, d, Ntp), bf)
-            for b in range(B):
-                ops.gemm(w[o + "wv"], xb[b * Ntp:(b + 1) * Ntp], out=vt[b], N=Ntp,
-                         in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
+            qk = ops.gemm(xb, w[o + "wqkv"], out=self._e((rows, 2 * d), f32), in_sumsq=xsq, vt_out=vt, vt_split=2 * d,
+                          vt_rows_per_batch=Ntp, **nrm)
             qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((rows, 2 * d), bf), rows=rows, d=d, nseg=2,
                                   ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
             att = self._e((rows, d), bf)
@@ -283,11 +283,9 @@ class Engine:
         # hoisted decoder K / V projections of the triangle tokens for ALL layers in two GEMMs
         # (view independent; every layer's kv_norm weight is folded into its rows)
         Lv = cfg.view_transformer_n_layers
-        k_all = ops.gemm(xb, w["dec.wk_all"], out_dtype=f32, in_sumsq=xsq, out_rscale=rsc, **nrm).view(B, Ntp, Lv * dv)
         v_all = self._e((B, Lv * dv, Ntp), bf)
-        for b in range(B):
-            ops.gemm(w["dec.wv_all"], xb[b * Ntp:(b + 1) * Ntp], out=v_all[b], N=Ntp,
-                     in_rscale=rsc[b * Ntp:(b + 1) * Ntp], scale_dim=1)
+        k_all = ops.gemm(xb, w["dec.wkv_all"], out=self._e((rows, Lv * dv), f32), in_sumsq=xsq, vt_out=v_all,
+                         vt_split=Lv * dv, vt_rows_per_batch=Ntp, **nrm).view(B, Ntp, Lv * dv)
         return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_all, v_all, dv)
 
     def alloc_scene_state(self, B: int, N: int) -> SceneState:
@@ -385,29 +383,18 @@ class Engine:
                           mask_bits=st.mask_bits[b], mask_bs=0)
             ops.gemm(att, w[o + "wout"], out=x, res1=x)
 
-            # self-attention among ray tokens  (layers/attention.py:515-523)
-            if cfg.view_transformer_use_swin_attn:
-                perm, region, _ = self._swin_maps(Hp, Wp, 0 if i % 2 == 0 else 4, V)
-                hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS, gather=perm)
-                qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
-                vt = ops.gemm(w[o + "s.wv"], hs, out=self._e((dv, rows), bf), N=rows)
-                qkn = ops.qknorm_rope(qk, w[o + "s.qkn"], self._e((rows, 2 * dv), bf), rows=rows, d=dv, nseg=2,
-                                      ldx=2 * dv, ldo=2 * dv, eps=EPS)
-                ops.attention(qkn, qkn[:, dv:], vt, att, B=1, H=Hh, Nq=rows, Nk=rows, ldq=2 * dv, ldk=2 * dv,
-                              ldvt=rows, ldo=dv, mode=1, group_id=region, group_period=Nr)
-                ops.gemm(att, w[o + "s.wo"], out=x, res1=x, row_map=perm)
-            else:
-                hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS)
-                qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
-                Nrp = _rup(Nr, 8)
-                vt = self._e((V, dv, Nrp), bf)
-                for vi in range(V):
-                    ops.gemm(w[o + "s.wv"], hs[vi * Nr:(vi + 1) * Nr], out=vt[vi], N=Nr)
-                qkn = ops.qknorm_rope(qk, w[o + "s.qkn"], self._e((rows, 2 * dv), bf), rows=rows, d=dv, nseg=2,
-                                      ldx=2 * dv, ldo=2 * dv, eps=EPS)  # ray RoPE is the identity
-                ops.attention(qkn, qkn[:, dv:], vt, att, B=V, H=Hh, Nq=Nr, Nk=Nr, ldq=2 * dv, ldk=2 * dv, ldvt=Nrp,
-                              ldo=dv, q_bs=Nr * 2 * dv, k_bs=Nr * 2 * dv, vt_bs=dv * Nrp, o_bs=Nr * dv)
-                ops.gemm(att, w[o + "s.wo"], out=x, res1=x)
+            # full self-attention among ray tokens  (layers/attention.py:515-523; swin runs in _decode_fused)
+            hs = ops.rmsnorm(x, w[o + "n_s"], self._e((rows, dv), bf), rows=rows, d=dv, eps=EPS)
+            qk = ops.gemm(hs, w[o + "s.wqk"], out_dtype=torch.float32)
+            Nrp = _rup(Nr, 8)
+            vt = self._e((V, dv, Nrp), bf)
+            for vi in range(V):
+                ops.gemm(w[o + "s.wv"], hs[vi * Nr:(vi + 1) * Nr], out=vt[vi], N=Nr)
+            qkn = ops.qknorm_rope(qk, w[o + "s.qkn"], self._e((rows, 2 * dv), bf), rows=rows, d=dv, nseg=2,
+                                  ldx=2 * dv, ldo=2 * dv, eps=EPS)  # ray RoPE is the identity
+            ops.attention(qkn, qkn[:, dv:], vt, att, B=V, H=Hh, Nq=Nr, Nk=Nr, ldq=2 * dv, ldk=2 * dv, ldvt=Nrp,
+                          ldo=dv, q_bs=Nr * 2 * dv, k_bs=Nr * 2 * dv, vt_bs=dv * Nrp, o_bs=Nr * dv)
+            ops.gemm(att, w[o + "s.wo"], out=x, res1=x)
             self._ffn(x, rows, dv, w[o + "n_f"], w[o + "w13"], w[o + "w2"])
             if i in cfg.out_layers:
                 feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
@@ -430,7 +417,6 @@ class Engine:
         xbw, xsqw = self._e((rows, dv), bf), self._e((rows, P), f32)
         qh, qsq = self._e((rows, dv), bf), self._e((rows, P), f32)
         qkh, qksq = self._e((rows, 2 * dv), bf), self._e((rows, 2 * P), f32)
-        rsw = self._e((rows,), f32)
         att = self._e((rows, dv), bf)
         vt = self._e((dv, rows), bf)
         Lv = cfg.view_transformer_n_layers
@@ -448,9 +434,8 @@ class Engine:
             # x += out_proj(att); bf16 copy + row sums land in window order for the swin block
             ops.gemm(att, w[o + "wout"], out=x, res1=x, out_sumsq=xsqw, out16=xbw, aux_row_map=inv)
             # shifted-window self-attention (window-major rows); q sums in parts [0,P), k sums in [P,2P)
-            ops.gemm(xbw, w[o + "s.wqk"], out16=qkh, col_mul=w[o + "s.qkn"], out_sumsq=qksq, in_sumsq=xsqw,
-                     out_rscale=rsw, **nrm)
-            ops.gemm(w[o + "s.wv"], xbw, out=vt, N=rows, in_rscale=rsw, scale_dim=1)
+            ops.gemm(xbw, w[o + "s.wqkv"], out16=qkh, col_mul=w[o + "s.qkn"], out_sumsq=qksq, in_sumsq=xsqw,
+                     vt_out=vt, vt_split=2 * dv, **nrm)
             ops.attention(qkh, qkh[:, dv:], vt, att, B=1, H=Hh, Nq=rows, Nk=rows, ldq=2 * dv, ldk=2 * dv,
                           ldvt=rows, ldo=dv, mode=1, group_id=region, group_period=Nr,
                           q_sumsq=qksq, k_sumsq=qksq.view(-1)[P:], sumsq_ld=2 * P, sumsq_parts=P, **nrm)

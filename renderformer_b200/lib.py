@@ -43,6 +43,8 @@ class GemmArgs(C.Structure):
         ("out_rscale", C.c_void_p), ("out_sumsq", C.c_void_p), ("out_sumsq_ld", C.c_int),
         ("out16", C.c_void_p), ("out16_dtype", C.c_int), ("ld16", C.c_longlong),
         ("col_mul", C.c_void_p), ("aux_row_map", C.c_void_p),
+        ("vt_out", C.c_void_p), ("vt_dtype", C.c_int), ("vt_split", C.c_int), ("vt_rows_per_batch", C.c_int),
+        ("vt_ld", C.c_longlong), ("vt_batch_stride", C.c_longlong),
     ]
 
 

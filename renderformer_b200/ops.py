@@ -50,7 +50,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
          bias=None, res1=None, res2=None, out_act=None, row_map=None, epi=L.EPI_STORE, out_dtype=None,
          conv=None, w2=None, b2=None, lda=None, ldw=None, ldo=None, ldres=None, bn=0,
          in_sumsq=None, in_rscale=None, scale_dim=0, norm_dim=0, norm_eps=1e-6, out_rscale=None, out_sumsq=None,
-         out16=None, col_mul=None, aux_row_map=None) -> torch.Tensor:
+         out16=None, col_mul=None, aux_row_map=None, vt_out=None, vt_split=0, vt_rows_per_batch=0) -> torch.Tensor:
     """out[M,N] = A[M,K] @ W[N,K]^T with fused epilogue.  `conv=(B,H,W,Cin)` switches A to NHWC 3x3
     implicit GEMM.  Shapes default to the tensors' 2-D shapes."""
     _need_cuda(A, W)
@@ -93,6 +93,11 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
     if out16 is not None:
         a.out16, a.out16_dtype, a.ld16 = out16.data_ptr(), _DT[out16.dtype], out16.stride(0)
     a.col_mul, a.aux_row_map = _p(col_mul), _p(aux_row_map)
+    if vt_out is not None:  # [dims, rows] or [batch, dims, rows_per_batch]: transposed V part (columns >= vt_split)
+        a.vt_out, a.vt_dtype, a.vt_split = vt_out.data_ptr(), _DT[vt_out.dtype], vt_split
+        a.vt_ld = vt_out.stride(-2)
+        a.vt_rows_per_batch = vt_rows_per_batch
+        a.vt_batch_stride = vt_out.stride(0) if vt_out.dim() == 3 else 0
     a.bias = _p(bias)
     if res1 is not None:
         a.res1, a.res_dtype = res1.data_ptr(), _DT[res1.dtype]
