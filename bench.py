@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from Python (N=1 only)")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from Python")
+    ap.add_argument("--view-chunk", type=int, default=0, help="views per decoder pass (0 = all of a GPU's views)")
+    ap.add_argument("--view-streams", type=int, default=1, help="CUDA streams the view chunks are spread over")
     ap.add_argument("--torch-cuda", action="store_true",
                     help="also time the oracle port on cuda:0 with torch kernels under bf16 autocast "
                          "(context: what the reference's PyTorch CUDA path costs on this GPU)")
@@ -198,7 +200,8 @@ def main():
     pipe.to(dev)
     eng = model.engine()
     Vl, R, N = args.views_per_gpu, args.resolution, args.tris
-    pipe.view_chunk = Vl
+    pipe.view_chunk = args.view_chunk or Vl
+    pipe.view_streams = args.view_streams
 
     scene = make_scene(N, Vl * world, seed=0)
     host = {k: v.pin_memory() for k, v in scene.items()}

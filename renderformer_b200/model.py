@@ -128,6 +128,11 @@ class RenderFormerRenderingPipeline:
         # cost (dominant for small scenes / low resolutions) and shrinks the gaps between kernels.
         # The returned tensor is then the graph's static output: valid until the next call with the
         # same signature.  Each cached graph pins its activations (a few GB for Large at 512^2).
+        # Independent view chunks can run on several CUDA streams: kernels of different chunks then fill
+        # each other's partial last waves and ramp-up / drain bubbles (every kernel here occupies a whole
+        # SM per CTA).  1 = sequential chunks.
+        self.view_streams = 1
+        self._side_streams = []
         self.cuda_graphs = False
         self.max_cached_graphs = 4
         self._graphs = {}
@@ -167,10 +172,38 @@ class RenderFormerRenderingPipeline:
             return self._graph_entry(("views", id(eng), id(state), resolution, self.view_chunk) + self._sig((c2w, fov)),
                                      (c2w, fov), lambda a, b: self.render_views(state, a, b, resolution, _eager=True))
         B, V = c2w.shape[:2]
+        jobs = [(b, v0) for b in range(B) for v0 in range(0, V, self.view_chunk)]
+        n_str = min(self.view_streams, len(jobs))
+        if n_str <= 1:
+            res = [eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
+                                    resolution) for b, v0 in jobs]
+        else:
+            dev = self.device
+            while len(self._side_streams) < n_str:
+                self._side_streams.append(torch.cuda.Stream(dev))
+            cur = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            res, joins = [], []
+            for i, (b, v0) in enumerate(jobs):
+                side = self._side_streams[i % n_str]
+                if i < n_str:
+                    side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    img = eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
+                                           resolution)
+                img.record_stream(cur)
+                res.append(img)
+            for side in self._side_streams[:n_str]:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                joins.append(ev)
+            for ev in joins:
+                cur.wait_event(ev)
         out = []
+        per_b = len(jobs) // B
         for b in range(B):
-            chunks = [eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
-                                       resolution) for v0 in range(0, V, self.view_chunk)]
+            chunks = res[b * per_b:(b + 1) * per_b]
             out.append(torch.cat(chunks, dim=0) if len(chunks) > 1 else chunks[0])
         return torch.stack(out, dim=0)
 

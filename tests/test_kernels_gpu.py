@@ -201,3 +201,22 @@ def test_model_forward_reference_signature():
     g = {k: v.cuda() for k, v in sc.items()}
     cam = pipe(g["triangles"], g["texture"], g["mask"], g["vn"], g["c2w"], g["fov"], resolution=R).cpu()
     assert hdr_rel_err(hdr, cam) < 3e-3  # same kernels; rays / transforms computed on the host here
+
+
+def test_view_chunks_on_several_streams():
+    """view_streams > 1 (independent view chunks on side streams, eager and under graph capture) returns
+    exactly the sequential result."""
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, _ = _pipe(cfg, 4)
+    sc = {k: v.cuda() for k, v in make_scene(50, 5, seed=8, pad_to=56).items()}
+
+    def call():
+        return pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=64).clone()
+    pipe.view_chunk = 8
+    want = call()
+    pipe.view_chunk, pipe.view_streams = 2, 2
+    assert torch.equal(call(), want)
+    pipe.view_chunk, pipe.view_streams = 1, 3
+    assert torch.equal(call(), want)
+    pipe.cuda_graphs = True
+    assert torch.equal(call(), want) and torch.equal(call(), want)
