@@ -312,6 +312,24 @@ def main():
                           "copies of neighbouring steps overlap the kernels)",
                    "single_call": {"value": frames / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
                                    "api": "RenderFormerRenderingPipeline.render, one blocking call per step"}}
+        else:
+            from renderformer_b200.dist import render_stream_sharded
+            host_scene = {k: host[k] for k in ("triangles", "texture", "mask", "vn", "c2w", "fov")}
+
+            def stream_steps(n):
+                sink = 0.0
+                for _mine, img in render_stream_sharded(pipe, (host_scene for _ in range(n)), resolution=R):
+                    sink += float(img[0, 0, 0, 0, 0])
+                return sink
+
+            stream_steps(3)
+            ms_stream = timed(lambda: stream_steps(args.steps), 1) / args.steps
+            e2e = {"value": frames / (ms_stream * 1e-3), "unit": UNIT, "ms_per_step": ms_stream,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(world * out_host.numel() * 4),
+                   "api": "renderformer_b200.dist.render_stream_sharded (rank 0 uploads the scene, NCCL broadcast of "
+                          "the scene state, every rank renders and downloads its own views; copies overlap kernels)",
+                   "single_call": {"value": frames / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
+                                   "api": "one blocking step per scene"}}
 
     roofline = None
     if not args.no_roofline and rank == 0:

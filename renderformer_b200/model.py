@@ -136,6 +136,7 @@ class RenderFormerRenderingPipeline:
         self.cuda_graphs = False
         self.max_cached_graphs = 4
         self._graphs = {}
+        self._static_states = {}
         self.replayed_launches = 0  # kernels launched through graph replays (bench.py's gpu_launches)
 
     @classmethod
@@ -267,11 +268,16 @@ class RenderFormerRenderingPipeline:
         return self._graph_entry(("render", id(eng), resolution, self.view_chunk) + self._sig(inputs), inputs, run)
 
     def static_scene_state(self, B: int, N: int) -> SceneState:
-        """A persistent SceneState (receive buffer of the NCCL broadcast on ranks that do not encode);
+        """The persistent SceneState of this shape (receive buffer of the NCCL broadcast on ranks that do
+        not encode; one per (B, N), reused by every call so that graphs captured on it stay valid);
         `render_views` on it is replayed from a CUDA graph when `cuda_graphs` is on."""
-        st = self.model.engine().alloc_scene_state(B, N)
-        st.static = True
-        return st
+        eng = self.model.engine()
+        key = (id(eng), B, N)
+        if key not in self._static_states:
+            st = eng.alloc_scene_state(B, N)
+            st.static = True
+            self._static_states[key] = st
+        return self._static_states[key]
 
     def __call__(self, *args, **kwargs):
         return self.render(*args, **kwargs)

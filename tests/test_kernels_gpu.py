@@ -220,3 +220,18 @@ def test_view_chunks_on_several_streams():
     assert torch.equal(call(), want)
     pipe.cuda_graphs = True
     assert torch.equal(call(), want) and torch.equal(call(), want)
+
+
+def test_render_stream_sharded_single_rank():
+    """dist.render_stream_sharded without a process group (world 1) = render_stream."""
+    from renderformer_b200.dist import render_stream_sharded
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, _ = _pipe(cfg, 9)
+    scenes = [{k: t.pin_memory() for k, t in make_scene(n, v, seed=s, pad_to=p).items()}
+              for n, v, s, p in ((40, 2, 1, 48), (70, 3, 2, None), (40, 2, 3, 48))]
+    want = [x.clone() for x in pipe.render_stream(iter(scenes), resolution=64)]
+    pipe.cuda_graphs = True
+    got = [(sl, x.clone()) for sl, x in render_stream_sharded(pipe, iter(scenes), resolution=64)]
+    assert len(got) == len(want)
+    for (sl, a), b, sc in zip(got, want, scenes):
+        assert sl == slice(0, sc["c2w"].shape[1]) and torch.equal(a, b)
