@@ -234,6 +234,10 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long idx, con
 constexpr int EK_GENERIC = 0;
 constexpr int EK_RESID = 1;   // out f32 = acc*r + res1 f32, + bf16 copy + partial sums of squares
 constexpr int EK_PROJ16 = 2;  // out16 bf16 = acc*r*col_mul only, + partial sums of squares
+// EK >= EK_CONV: the generic epilogue with its flags fixed at compile time for the DPT convolutions
+// (fp16 in / out, 128-wide tile): EK = EK_CONV + mask, mask bits below
+constexpr int EK_CONV = 16;
+constexpr int CF_OUT = 1, CF_ACT = 2, CF_BIAS = 4, CF_RES1 = 8, CF_RES2 = 16;
 
 __device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, float& hi) {
   if (dtype == RFB_BF16) {
@@ -250,6 +254,7 @@ __device__ __forceinline__ void unpack16x2(uint32_t u, int dtype, float& lo, flo
 // one straight-line pass over the 8 row slots per feature ("loop fission"), so a flag costs one
 // uniform branch per chunk instead of one per row slot and each pass schedules as a block.
 // ---------------------------------------------------------------------------------------------
+template <int EK>
 __device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p, float* stage, int lane,
                                                            uint32_t taddr0, int n0, int c_begin, int c_end,
                                                            int orow_mine, int arow_mine, float rs_mine,
@@ -263,10 +268,20 @@ __device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p,
     orow[it] = __shfl_sync(0xffffffffu, orow_mine, it * 4 + g4);
     rs[it] = __shfl_sync(0xffffffffu, rs_mine, it * 4 + g4);
   }
-  const bool f_out = p.out != nullptr, f_res = p.res1 != nullptr, f_res32 = p.res_dtype == RFB_F32;
-  const bool f_res2 = p.res2 != nullptr, f_out16 = p.out16 != nullptr, f_sumsq = p.out_sumsq != nullptr;
-  const bool f_act = p.out_act != nullptr, f_bias = p.bias != nullptr, f_cm = p.col_mul != nullptr;
-  const bool f_cs = p.in_rscale != nullptr && p.scale_dim == 1;
+  constexpr bool RT = EK < EK_CONV;  // flags read at run time
+  constexpr int CM = RT ? 0 : EK - EK_CONV;
+  const bool f_out = RT ? p.out != nullptr : (CM & CF_OUT) != 0;
+  const bool f_res = RT ? p.res1 != nullptr : (CM & CF_RES1) != 0;
+  const bool f_res32 = RT ? p.res_dtype == RFB_F32 : false;
+  const bool f_res2 = RT ? p.res2 != nullptr : (CM & CF_RES2) != 0;
+  const bool f_out16 = RT ? p.out16 != nullptr : false;
+  const bool f_sumsq = RT ? p.out_sumsq != nullptr : false;
+  const bool f_act = RT ? p.out_act != nullptr : (CM & CF_ACT) != 0;
+  const bool f_bias = RT ? p.bias != nullptr : (CM & CF_BIAS) != 0;
+  const bool f_cm = RT ? p.col_mul != nullptr : false;
+  const bool f_cs = RT ? (p.in_rscale != nullptr && p.scale_dim == 1) : false;
+  const int out_dtype = RT ? p.out_dtype : RFB_F16;
+  const int res_dtype = RT ? p.res_dtype : RFB_F16;
   float sqp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint4 cur[8], nxt[8];  // raw residual bits; 16-bit residuals: res1 in (x,y), res2 in (z,w)
   auto prefetch = [&](uint4(&r)[8], int n) {
@@ -335,25 +350,25 @@ __device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p,
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           float r0, r1, r2, r3;
-          unpack16x2(cur[it].x, p.res_dtype, r0, r1), unpack16x2(cur[it].y, p.res_dtype, r2, r3);
+          unpack16x2(cur[it].x, res_dtype, r0, r1), unpack16x2(cur[it].y, res_dtype, r2, r3);
           x[it][0] += r0, x[it][1] += r1, x[it][2] += r2, x[it][3] += r3;
         }
         if (f_res2) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float r0, r1, r2, r3;
-            unpack16x2(cur[it].z, p.res_dtype, r0, r1), unpack16x2(cur[it].w, p.res_dtype, r2, r3);
+            unpack16x2(cur[it].z, res_dtype, r0, r1), unpack16x2(cur[it].w, res_dtype, r2, r3);
             x[it][0] += r0, x[it][1] += r1, x[it][2] += r2, x[it][3] += r3;
           }
         }
       }
     }
     if (f_out) {
-      if (p.out_dtype == RFB_F32) {
+      if (out_dtype == RFB_F32) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           if (orow[it] >= 0 && col_ok) store4(p.out, RFB_F32, (long long)orow[it] * p.ldo + n, x[it]);
-      } else if (p.out_dtype == RFB_BF16) {
+      } else if (out_dtype == RFB_BF16) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           if (orow[it] >= 0 && col_ok) store4(p.out, RFB_BF16, (long long)orow[it] * p.ldo + n, x[it]);
@@ -384,12 +399,12 @@ __device__ __forceinline__ void epilogue_generic_coalesced(const GemmKParams& p,
       }
     }
     if (f_act) {
-      const bool bf = p.out_dtype == RFB_BF16;
+      const bool bf = out_dtype == RFB_BF16;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         float y[4] = {silu_f(x[it][0]), silu_f(x[it][1]), silu_f(x[it][2]), silu_f(x[it][3])};
         if (orow[it] >= 0 && col_ok) {
-          if (p.out_dtype == RFB_F32) store4(p.out_act, RFB_F32, (long long)orow[it] * p.ldo + n, y);
+          if (out_dtype == RFB_F32) store4(p.out_act, RFB_F32, (long long)orow[it] * p.ldo + n, y);
           else if (bf) store4(p.out_act, RFB_BF16, (long long)orow[it] * p.ldo + n, y);
           else store4(p.out_act, RFB_F16, (long long)orow[it] * p.ldo + n, y);
         }
@@ -717,7 +732,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
       if (p.vt_out && n0 >= p.vt_split) {  // tile of the transposed (V) part: warp-uniform per tile
         epilogue_vt_chunks(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, n0, c_begin, c_end,
                            mt * kBM + r, valid, rs, &tfull[as], aph);
-      } else if constexpr (EK != EK_GENERIC) {
+      } else if constexpr (EK == EK_RESID || EK == EK_PROJ16) {
         static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
         epilogue_half_tile_fast<EK>(p, my_stage, lane,
                                     tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
@@ -725,7 +740,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
       } else {
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
         if ((p.epi == RFB_EPI_STORE) && !p.direct_store) {
-          epilogue_generic_coalesced(p, my_stage, lane, taddr0, n0, c_begin, c_end, orow_mine, arow_mine, rs,
+          epilogue_generic_coalesced<EK>(p, my_stage, lane, taddr0, n0, c_begin, c_end, orow_mine, arow_mine, rs,
                                      &tfull[as], aph);
         } else {
           mbar_wait(&tfull[as], aph);
@@ -921,6 +936,24 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     if (a->out && a->out_dtype == RFB_F32 && a->res1 && a->res_dtype == RFB_F32 && !a->col_mul)
       return launch_gemm<256, EK_RESID>(tmA, tmB, p, grid, stream);
     if (!a->out && !a->res1 && a->col_mul) return launch_gemm<256, EK_PROJ16>(tmA, tmB, p, grid, stream);
+  }
+  if (bn == 128 && a->a_mode == RFB_A_CONV3X3 && a->epi == RFB_EPI_STORE && !p.direct_store && !fused_any && !a->vt_out &&
+      a->dtype == RFB_F16 && a->out_dtype == RFB_F16 && (!a->res1 || a->res_dtype == RFB_F16) && a->N % 128 == 0) {
+    const int cm = (a->out ? CF_OUT : 0) | (a->out_act ? CF_ACT : 0) | (a->bias ? CF_BIAS : 0) | (a->res1 ? CF_RES1 : 0) |
+                   (a->res2 ? CF_RES2 : 0);
+    switch (cm) {  // the flag sets the DPT head uses (layers/dpt.py:57-92,133-159,195-240)
+      case CF_OUT | CF_ACT: return launch_gemm<128, EK_CONV + (CF_OUT | CF_ACT)>(tmA, tmB, p, grid, stream);
+      case CF_ACT | CF_BIAS: return launch_gemm<128, EK_CONV + (CF_ACT | CF_BIAS)>(tmA, tmB, p, grid, stream);
+      case CF_OUT | CF_BIAS | CF_RES1:
+        return launch_gemm<128, EK_CONV + (CF_OUT | CF_BIAS | CF_RES1)>(tmA, tmB, p, grid, stream);
+      case CF_OUT | CF_ACT | CF_BIAS | CF_RES1:
+        return launch_gemm<128, EK_CONV + (CF_OUT | CF_ACT | CF_BIAS | CF_RES1)>(tmA, tmB, p, grid, stream);
+      case CF_OUT | CF_BIAS | CF_RES1 | CF_RES2:
+        return launch_gemm<128, EK_CONV + (CF_OUT | CF_BIAS | CF_RES1 | CF_RES2)>(tmA, tmB, p, grid, stream);
+      case CF_OUT | CF_ACT | CF_BIAS | CF_RES1 | CF_RES2:
+        return launch_gemm<128, EK_CONV + (CF_OUT | CF_ACT | CF_BIAS | CF_RES1 | CF_RES2)>(tmA, tmB, p, grid, stream);
+      default: break;
+    }
   }
   switch (bn) {
     case 32: return launch_gemm<32>(tmA, tmB, p, grid, stream);
