@@ -795,6 +795,207 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return check_launch("gemm_tc_kernel");
 }
 
+// =============================================================================================
+// 3x3 convolution with a shared-memory halo tile.
+//
+// The implicit-GEMM conv above re-loads the activation tile once per filter tap (9x) and the weights
+// once per 128-pixel tile; both come from L2 and the kernel ends up bound by L2->SM bandwidth.  Here a
+// CTA works on a 16 x 16 pixel super-tile = two 8-wide x 16-tall UMMA tiles: per 64-channel block ONE
+// 4-D TMA box brings the 18 x 18 pixel halo region into shared memory (pixel = 128-byte row, 128B
+// swizzle), and the nine tap-shifted A operands of both tiles are read straight out of it by offsetting
+// the UMMA descriptor: start = halo + ((dy*18 + dx + 8*tile) * 128) B, 8-row-group stride = 18 * 128 B.
+// (The swizzle is a function of the shared-memory address, so any 128-byte-aligned start and any group
+// stride work -- checked by selftest_halo.)  A weight stage [BN x 64] is used for both tiles, so per
+// 256 output pixels and channel block 41.5 KB + 9 * BN * 128 B travel instead of 2 * 9 * (16 KB + BN*128 B).
+// Accumulators: 2 tiles x 2 buffers x BN TMEM columns.  Epilogues are the GEMM's.
+// =============================================================================================
+constexpr int kHaloPitch = 18;                                   // pixels per halo row
+constexpr uint32_t kHaloBytes = kHaloPitch * kHaloPitch * 128;   // 41472
+constexpr uint32_t kHaloStride = 42 * 1024;                      // 1024-aligned slot per halo buffer
+
+template <int BN>
+struct HaloCfg {
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr uint32_t kTmemCols = (4 * BN < 32) ? 32 : 4 * BN;
+  static constexpr uint32_t kSmemBytes = 2 * kHaloStride + kStages * kBBytes + 1024 + 256 + kEpiStageBytes;
+};
+
+template <int BN, int EK>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmKParams p) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr uint32_t B_BYTES = Cfg::kBBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sH = smem;                      // 2 halo buffers
+  uint8_t* sB = smem + 2 * kHaloStride;    // weight stages
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* bempty = bfull + STAGES;
+  uint64_t* hfull = bempty + STAGES;
+  uint64_t* hempty = hfull + 2;
+  uint64_t* tfull = hempty + 2;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bfull) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bfull[i], 1), mbar_init(&bempty[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hfull[i], 1), mbar_init(&hempty[i], 1);
+      mbar_init(&tfull[i], 1), mbar_init(&tempty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int total = p.num_m_tiles;  // super-tiles
+  const int ncb = p.kb_per_tap;     // 64-channel blocks
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, hb = 0;
+      uint32_t phase = 0, hphase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int bi = tile / per_img, rr = tile % per_img;
+        const int y0 = (rr / p.tiles_x) * 16, x0 = (rr % p.tiles_x) * 16;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(&hempty[hb], hphase ^ 1);
+          mbar_expect_tx(&hfull[hb], kHaloBytes);
+          tma_load_4d(sH + hb * kHaloStride, &tmA, &hfull[hb], cb * kBK, x0 - 1, y0 - 1, bi);
+          if (++hb == 2) hb = 0, hphase ^= 1;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bempty[stage], phase ^ 1);
+            mbar_expect_tx(&bfull[stage], B_BYTES);
+            tma_load_2d(sB + stage * B_BYTES, &tmB, &bfull[stage], tap * p.Cin + cb * kBK, 0);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, hb = 0, it = 0;
+      uint32_t phase = 0, hphase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + as * 2 * BN;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(&hfull[hb], hphase);
+          tc_fence_after();
+          const uint32_t halo = smem_u32(sH + hb * kHaloStride);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bfull[stage], phase);
+            tc_fence_after();
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+            const uint32_t a0 = halo + ((tap / 3) * kHaloPitch + tap % 3) * 128;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              // 8-row group g = image row y of the tile: stride = one halo row
+              uint64_t ad = static_cast<uint64_t>(((a0 + t * 8 * 128) >> 4) & 0x3fff);
+              ad |= static_cast<uint64_t>((kHaloPitch * 128) >> 4) << 32;
+              ad |= static_cast<uint64_t>(1) << 46;
+              ad |= static_cast<uint64_t>(2) << 61;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_f16(d0 + t * BN, ad + 2 * k, bd + 2 * k, p.idesc, (cb | tap | k) != 0);
+            }
+            umma_commit(&bempty[stage]);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+          umma_commit(&hempty[hb]);
+          if (++hb == 2) hb = 0, hphase ^= 1;
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (same code as the GEMM) ------------------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int bi = tile / per_img, rr = tile % per_img;
+      const int y = (rr / p.tiles_x) * 16 + (r >> 3);
+      float* my_stage = epi_stage + (warp - 2) * 32 * 32;
+      constexpr int NCH = BN / 32;
+      constexpr int HALF = (NCH + 1) / 2;
+      const int c_begin = ((warp - 2) >> 2) * HALF;
+      const int c_end = (c_begin + HALF < NCH) ? c_begin + HALF : NCH;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int x = (rr % p.tiles_x) * 16 + t * 8 + (r & 7);
+        const bool valid = (y < p.H) && (x < p.Wd);
+        const long long orow = (static_cast<long long>(bi) * p.H + y) * p.Wd + x;
+        const int orow_mine = valid ? static_cast<int>(orow) : -1;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 2 * BN + t * BN;
+        if (p.epi == RFB_EPI_STORE) {
+          epilogue_generic_coalesced<EK>(p, my_stage, lane, taddr0, 0, c_begin, c_end, orow_mine, orow_mine, 1.0f,
+                                         &tfull[as], aph);
+        } else {
+          mbar_wait(&tfull[as], aph);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; ++c) {
+            if (c * 32 >= p.n_store) break;
+            uint32_t v[32];
+            tmem_ld32(taddr0 + c * 32, v);
+            tmem_wait_ld();
+            if (valid) epilogue_chunk(p, orow, c * 32, v, 1.0f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EK = EK_GENERIC>
+static int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
+                            cudaStream_t stream) {
+  using Cfg = HaloCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::kSmemBytes) != cudaSuccess)
+      return RFB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  conv_halo_kernel<BN, EK><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  g_launch_count++;
+  return check_launch("conv_halo_kernel");
+}
+
 }  // namespace rfb
 
 using namespace rfb;
@@ -893,6 +1094,55 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     if (a->B <= 0 || a->H <= 0 || a->Wd <= 0 || a->Cin <= 0 || a->K != 9 * a->Cin ||
         a->M != a->B * a->H * a->Wd || a->row_map)
       return RFB_ERR_ARG;
+    {
+      // halo-tile kernel: whole 64-channel blocks, one N tile, enough 16 x 16 super-tiles to fill the GPU
+      static int halo_on = -1;
+      if (halo_on < 0) {
+        const char* e = getenv("RFB_CONV_HALO");
+        halo_on = (e && e[0] == '0') ? 0 : 1;
+      }
+      const int stx = (a->Wd + 15) / 16, sty = (a->H + 15) / 16;
+      const long long n_super = (long long)a->B * stx * sty;
+      if (halo_on && a->Cin % 64 == 0 && a->N == bn && (bn == 128 || bn == 64 || bn == 32) && n_super >= 96 &&
+          !fused_any && !a->vt_out && !p.direct_store) {
+        p.H = a->H, p.Wd = a->Wd, p.Cin = a->Cin;
+        p.tw = 8, p.th = 16, p.tiles_x = stx, p.tiles_y = sty, p.kb_per_tap = a->Cin / kBK;
+        p.num_m_tiles = (int)n_super, p.num_n_tiles = 1, p.num_kb = 9 * p.kb_per_tap;
+        uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->B};
+        uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->Wd * a->Cin * 2, (uint64_t)a->H * a->Wd * a->Cin * 2};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)kHaloPitch, (uint32_t)kHaloPitch, 1};
+        if ((rc = make_tmap_16b(&tmA, a->dtype, a->A, 4, dims, strides, box)) != RFB_OK) return rc;
+        uint64_t wd[2] = {(uint64_t)a->K, (uint64_t)a->N};
+        uint64_t ws[1] = {(uint64_t)a->ldw * 2};
+        uint32_t wb[2] = {(uint32_t)kBK, (uint32_t)bn};
+        if ((rc = make_tmap_16b(&tmB, a->dtype, a->W, 2, wd, ws, wb)) != RFB_OK) return rc;
+        p.idesc = umma_idesc_f16(a->dtype == RFB_BF16 ? 1u : 0u, kBM, bn);
+        const int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+        const int grid = (int)(n_super < cap ? n_super : cap);
+        if (bn == 64) return launch_conv_halo<64>(tmA, tmB, p, grid, stream);
+        if (bn == 32) return launch_conv_halo<32>(tmA, tmB, p, grid, stream);
+        if (a->epi == RFB_EPI_STORE && a->dtype == RFB_F16 && a->out_dtype == RFB_F16 &&
+            (!a->res1 || a->res_dtype == RFB_F16)) {
+          const int cm = (a->out ? CF_OUT : 0) | (a->out_act ? CF_ACT : 0) | (a->bias ? CF_BIAS : 0) |
+                         (a->res1 ? CF_RES1 : 0) | (a->res2 ? CF_RES2 : 0);
+          switch (cm) {
+            case CF_OUT | CF_ACT: return launch_conv_halo<128, EK_CONV + (CF_OUT | CF_ACT)>(tmA, tmB, p, grid, stream);
+            case CF_ACT | CF_BIAS: return launch_conv_halo<128, EK_CONV + (CF_ACT | CF_BIAS)>(tmA, tmB, p, grid, stream);
+            case CF_OUT | CF_BIAS | CF_RES1:
+              return launch_conv_halo<128, EK_CONV + (CF_OUT | CF_BIAS | CF_RES1)>(tmA, tmB, p, grid, stream);
+            case CF_OUT | CF_ACT | CF_BIAS | CF_RES1:
+              return launch_conv_halo<128, EK_CONV + (CF_OUT | CF_ACT | CF_BIAS | CF_RES1)>(tmA, tmB, p, grid, stream);
+            case CF_OUT | CF_BIAS | CF_RES1 | CF_RES2:
+              return launch_conv_halo<128, EK_CONV + (CF_OUT | CF_BIAS | CF_RES1 | CF_RES2)>(tmA, tmB, p, grid, stream);
+            case CF_OUT | CF_ACT | CF_BIAS | CF_RES1 | CF_RES2:
+              return launch_conv_halo<128, EK_CONV + (CF_OUT | CF_ACT | CF_BIAS | CF_RES1 | CF_RES2)>(tmA, tmB, p, grid,
+                                                                                                   stream);
+            default: break;
+          }
+        }
+        return launch_conv_halo<128>(tmA, tmB, p, grid, stream);
+      }
+    }
     p.H = a->H, p.Wd = a->Wd, p.Cin = a->Cin;
     p.tw = (a->Wd >= 16) ? 16 : 8;
     p.th = kBM / p.tw;

@@ -475,6 +475,12 @@ int main(int argc, char** argv) {
         {"conv3x3 f16 1x20x24 96->64 ragged", 480, 64, 9 * 96, RFB_F16, C3, 1, 20, 24, 96, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
         {"conv3x3 f16 1x64x64 128->64 bn64", 4096, 64, 9 * 128, RFB_F16, C3, 1, 64, 64, 128, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
         {"conv3x3 f16 final 1x64x64 64->32->3", 4096, 32, 9 * 64, RFB_F16, C3, 1, 64, 64, 64, RFB_EPI_FINAL, RFB_F32, 1, 0, 0, 0, 0, RFB_F16, 0},
+        // large enough for the halo-tile kernel (>= 96 super-tiles of 16 x 16 pixels)
+        {"conv3x3 halo 1x176x160 128->128 bias res2 act", 176 * 160, 128, 9 * 128, RFB_F16, C3, 1, 176, 160, 128, RFB_EPI_STORE, RFB_F16, 1, 1, 1, 1, 0, RFB_F16, 0},
+        {"conv3x3 halo 1x170x150 128->128 ragged, act", 170 * 150, 128, 9 * 128, RFB_F16, C3, 1, 170, 150, 128, RFB_EPI_STORE, RFB_F16, 0, 0, 0, 1, 0, RFB_F16, 0},
+        {"conv3x3 halo 2x100x140 64->64 bias", 2 * 100 * 140, 64, 9 * 64, RFB_F16, C3, 2, 100, 140, 64, RFB_EPI_STORE, RFB_F16, 1, 0, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 halo 1x160x144 256->128 bias res1", 160 * 144, 128, 9 * 256, RFB_F16, C3, 1, 160, 144, 256, RFB_EPI_STORE, RFB_F16, 1, 1, 0, 0, 0, RFB_F16, 0},
+        {"conv3x3 halo final 1x160x160 64->32->3", 160 * 160, 32, 9 * 64, RFB_F16, C3, 1, 160, 160, 64, RFB_EPI_FINAL, RFB_F32, 1, 0, 0, 0, 0, RFB_F16, 0},
     };
     int n = quick ? 3 : (int)cases.size();
     for (int i = 0; i < n; ++i) run_case(cases[i]);
@@ -512,6 +518,8 @@ int main(int argc, char** argv) {
     bench_fused("dec s.wqk: insq+out16+sumsq ", 16384, 2048, 1024, false, true, true, true, false, false);
     bench_fused("plain res only              ", 16384, 1024, 1024, true, false, false, false, false, true);
     bench_fused("plain f32 store only        ", 16384, 1024, 1024, false, false, false, false, false, true);
+    bench("conv 4x256^2 128->128", 262144, 128, 1152, RFB_EPI_STORE, RFB_F16, 128, 256, 128, 4);
+    bench("conv 4x512^2 128->64 ", 1048576, 64, 1152, RFB_EPI_STORE, RFB_F16, 64, 512, 128, 4);
     bench("conv 256^2 128->128", 65536, 128, 1152, RFB_EPI_STORE, RFB_F16, 128, 256, 128);
     bench("conv 512^2 128->64 ", 262144, 64, 1152, RFB_EPI_STORE, RFB_F16, 64, 512, 128);
   }
