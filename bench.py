@@ -354,11 +354,11 @@ def main():
         att = by.get("attention", [0.0, 1.0, 1])
         ach = g[0] / g[1] / 1e12
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01e_gemm_traffic.json")
         if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, Vl) == (4096, 512, 4):
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01d_gemm_traffic.json (ncu dram__bytes_read+write, avg over one step's GEMM launches)"
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01e_gemm_traffic.json (ncu dram__bytes_read+write, avg over one step's GEMM launches)"
         roofline = {
             "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,

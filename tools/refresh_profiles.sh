@@ -9,7 +9,7 @@ out=gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-cuda-graphs"   # eager launches: same kernels, simple launch order
 $B > $out/${tag}_bench_plain.json 2> $out/${tag}_bench_plain.err || { echo "plain bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 600 -c 215 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_launches.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "regex:gemm_tc|conv_halo" \
     --launch-skip 155 -c 155 --csv --log-file $out/${tag}_gemm_traffic.csv $B > $out/${tag}_ncu_traffic.log 2>&1
 P="python tools/profile_step.py"
 # GEMM launch order inside a step (Large): 51 scene-stage GEMMs, then the ray-token GEMM, then per decoder
