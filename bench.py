@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""Headline benchmark: frames/sec of the RenderFormer-V1.1-swin-Large forward pass on synthetic
-4096-triangle scenes at 512x512 (BASELINE.json metric), N GPUs of one node.
+"""Headline benchmark: frames/sec of the RenderFormer-V1.1-swin-Large forward pass on a synthetic
+4096-triangle scene at 512x512 (BASELINE.json metric), N GPUs of one node.
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...   # CPU arm: the oracle port of the reference's PyTorch path
+    python bench.py --impl reference ...   # CPU arm: the UNMODIFIED reference's PyTorch path on the host cores
 
-One step = one scene through both stages: rank 0 runs the view-independent stage once, the
-per-layer triangle K/V is broadcast with NCCL, every rank renders `--views-per-gpu` views of a
-camera orbit, images are gathered on rank 0 (weak scaling: per-GPU work is fixed).
-Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md §Measurement).
+One step = ONE JOB of fixed size: one scene through the view-independent stage and `--total-views`
+(32: BASELINE configs[2]) camera views of an orbit through the view-dependent stage, at any N
+("scaling": "strong").  At N > 1 the scene stage is row-sharded over the ranks (one NCCL all-gather per
+encoder layer), every rank renders total_views / N views, the images are gathered on rank 0.
+`--views-per-gpu V` switches to the weak-scaling job (V views on every GPU).
+Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md §5).
 """
 from __future__ import annotations
 
@@ -39,22 +41,22 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="v1_1_swin_large")
     ap.add_argument("--tris", type=int, default=4096)
     ap.add_argument("--resolution", type=int, default=512)
-    ap.add_argument("--views-per-gpu", type=int, default=4)
+    ap.add_argument("--total-views", type=int, default=32, help="views of the fixed job (strong scaling)")
+    ap.add_argument("--views-per-gpu", type=int, default=0, help="> 0: weak scaling, this many views on every GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-on-CUDA context arm (N=1 only)")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from Python")
-    ap.add_argument("--view-chunk", type=int, default=0, help="views per decoder pass (0 = all of a GPU's views)")
+    ap.add_argument("--view-chunk", type=int, default=4, help="views per decoder pass")
     ap.add_argument("--view-streams", type=int, default=1, help="CUDA streams the view chunks are spread over")
-    ap.add_argument("--torch-cuda", action="store_true",
-                    help="also time the oracle port on cuda:0 with torch kernels under bf16 autocast "
-                         "(context: what the reference's PyTorch CUDA path costs on this GPU)")
+    ap.add_argument("--ref-cuda-worker", default="", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -67,56 +69,193 @@ def load_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# --------------------------------------------------------------------------- CPU arm
-def cpu_sample(cfg_name: str, steps: int, warmup: int, full_tris: int, full_res: int, views_per_step: int):
-    """Time the oracle (CPU fp32 port of the reference's PyTorch path) on a bounded sample of the
-    workload and scale to the metric by algorithmic FLOPs.  Returns (frames/s, ms/step, cores, sample)."""
-    from oracle import renderformer_oracle as orc
-    from renderformer_b200.config import RenderFormerConfig
-    from renderformer_b200.flops import job_flops
-    from renderformer_b200.synth import init_state_dict, make_scene
+def job_views(args, world):
+    return args.views_per_gpu * world if args.views_per_gpu > 0 else args.total_views
 
+
+def workload_text(args, world):
+    V = job_views(args, world)
+    kind = (f"{args.views_per_gpu} views on every GPU (weak scaling)" if args.views_per_gpu > 0 else
+            f"fixed job of {V} views (strong scaling; BASELINE configs[2] at 32)")
+    return (f"{args.config} (483M, random-init weights, seed 7), synthetic {args.tris}-triangle scene (seed 0), "
+            f"{args.resolution}x{args.resolution}, one scene + {V}-view camera orbit per step: {kind}")
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _reference_or_port(cfg, sd):
+    """(render(scene, res) -> image, kind, description).  The unmodified reference when it can be imported
+    (baseline/_ref or /root/reference), else the oracle port."""
+    try:
+        from oracle.reference_loader import build_reference_pipeline
+        pipe, ref = build_reference_pipeline(cfg, sd, "cpu", "sdpa")
+
+        def render(sc, res):
+            return pipe(sc["triangles"], sc["texture"].clone(), sc["mask"], sc["vn"], sc["c2w"], sc["fov"],
+                        resolution=res, torch_dtype=torch.float32)
+        return render, "reference", f"unmodified reference from {os.path.relpath(ref, ROOT) if ref.startswith(ROOT) else ref}, " \
+                                    "RenderFormerRenderingPipeline(torch_dtype=float32), ATTN_IMPL=sdpa"
+    except Exception as e:  # noqa: BLE001  (reference not installed on this box)
+        from oracle import renderformer_oracle as orc
+
+        def render(sc, res):
+            return orc.render(sd, cfg, sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], res)
+        return render, "port", f"oracle port (reference unavailable: {str(e)[:80]})"
+
+
+def cpu_arm(args, views: int, steps: int, warm_small: bool = True):
+    """Time the reference's CPU path (fp32, all host threads) on `views` views of the bench scene at the
+    metric's own triangle count and resolution.  Returns a dict(value, ms, cores, kind, sample)."""
+    from renderformer_b200.config import RenderFormerConfig
+    from renderformer_b200.synth import init_state_dict, make_scene
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = RenderFormerConfig.named(cfg_name)
-    s_tris, s_res = min(full_tris, 1024), min(full_res, 128)
+    cfg = RenderFormerConfig.named(args.config)
     sd = init_state_dict(cfg, 7)
-    sc = make_scene(s_tris, 1, seed=0)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        orc.render(sd, cfg, sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], s_res)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+    render, kind, what = _reference_or_port(cfg, sd)
+    full = make_scene(args.tris, job_views(args, 1), seed=0)
+    sc = dict(full, c2w=full["c2w"][:, :views].contiguous(), fov=full["fov"][:, :views].contiguous())
+    with torch.no_grad():
+        if warm_small:  # thread pool / allocator warm-up on a small frame; the timed calls are full size
+            tiny = make_scene(64, 1, seed=1)
+            render(tiny, 64)
+        times = []
+        for _ in range(max(1, steps)):
+            t0 = time.perf_counter()
+            render(sc, args.resolution)
+            times.append(time.perf_counter() - t0)
     dt = statistics.median(times)
-    cpu_flops_per_s = job_flops(cfg, s_tris, s_res, 1, 1) / dt
-    step_flops = job_flops(cfg, full_tris, full_res, 1, views_per_step)
-    fps = views_per_step / (step_flops / cpu_flops_per_s)
-    sample = (f"oracle fp32 (torch CPU, {cores} threads): {cfg_name}, {s_tris} tris, 1 view {s_res}x{s_res} "
-              f"= {job_flops(cfg, s_tris, s_res, 1, 1) / 1e12:.3f} TFLOP in {dt:.2f} s "
-              f"({cpu_flops_per_s / 1e12:.3f} TFLOP/s), scaled by algorithmic FLOPs to "
-              f"{full_tris} tris, {views_per_step} views {full_res}x{full_res} per step")
-    return fps, dt * 1e3, cores, sample
+    return {"value": views / dt, "ms": dt * 1e3, "cores": cores, "kind": kind, "views": views,
+            "sample": f"{what}; {cores} torch threads; {args.tris} triangles, {views} of the job's views at "
+                      f"{args.resolution}x{args.resolution} in one call (scene stage + {views} views), "
+                      f"median of {len(times)} call(s): {dt:.2f} s"}
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (unmodified, baseline/_ref) on the metric's
+    config.  A step is the WHOLE job -- the scene and all of its views in one pipeline call, as the
+    reference's batch CLI issues it -- timed once after a small warm-up call (about 70 s on the GPU box's 16
+    cores, ~22 GB of host memory measured at 0.55 GB per view + 4 GB).  Only if the host has too little free
+    memory for that is a bounded sample used instead: the scene stage plus 8 of the job's views in one call,
+    whose per-frame figure is reported as is (the scene stage is then amortised over fewer views, which makes
+    the reference look ~8 % slower per frame than on the full job; `sample` says which was run)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, ms, cores, sample = cpu_sample(args.config, max(1, args.steps), min(args.warmup, 1), args.tris,
-                                        args.resolution, args.views_per_gpu)
+    V = job_views(args, max(1, args.gpus))
+    try:
+        import psutil
+        free_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:  # noqa: BLE001
+        free_gb = 0.0
+    full = free_gb >= 1.5 * (0.55 * V + 4.0) + 8.0
+    sample_views = V if full else min(V, 8)
+    steps = 1 if sample_views > 8 else min(max(1, args.steps), 2)
+    r = cpu_arm(args, sample_views, steps)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}, synthetic {args.tris}-tri scene, {args.resolution}x{args.resolution}, "
-                               f"{args.views_per_gpu} views/step (CPU arm: bounded sample, FLOP-scaled)"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
+        "scaling": "weak" if args.views_per_gpu > 0 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(args, max(1, args.gpus)),
+                   "timed": f"{steps} timed call(s) of scene + {sample_views} views "
+                            f"({'the whole job' if sample_views == V else f'bounded sample of the {V}-view job'}), "
+                            f"1 small warm-up call; the driver's --steps/--warmup are capped to keep the run within minutes"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- reference on CUDA (context)
+def ref_cuda_worker(args):
+    """Subprocess body: the UNMODIFIED reference on cuda:0 through its own pipeline API, same scene / weights
+    / job as the bench step.  Variants: its shipped default for bf16 (`torch_dtype=bfloat16`:
+    encoder bf16, view transformer fp32/TF32 with forced SDPA, allow_tf32 as batch_infer.py:86-87), and the
+    'fair bf16' call of model.forward(tf32_view_tf=False) under bf16 autocast.  Prints one JSON line."""
+    attn = args.ref_cuda_worker
+    out = {"attn_impl": attn}
+    try:
+        from oracle.reference_loader import build_reference_pipeline
+        from renderformer_b200.config import RenderFormerConfig
+        from renderformer_b200.metrics import hdr_rel_err
+        from renderformer_b200.synth import init_state_dict, make_scene
+        dev = torch.device("cuda:0")
+        cfg = RenderFormerConfig.named(args.config)
+        pipe, ref = build_reference_pipeline(cfg, init_state_dict(cfg, 7), dev, attn)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        V = job_views(args, 1)
+        sc = {k: v.to(dev) for k, v in make_scene(args.tris, V, seed=0).items()}
+        chunk = min(V, 8)  # views per pipeline call (the reference re-runs its encoder in every call)
+
+        def timed(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        def default_call(v0=0, nv=V):
+            return pipe(sc["triangles"], sc["texture"].clone(), sc["mask"], sc["vn"], sc["c2w"][:, v0:v0 + nv],
+                        sc["fov"][:, v0:v0 + nv], resolution=args.resolution, torch_dtype=torch.bfloat16)
+
+        def job(call):
+            try:
+                return [call(0, V)]
+            except torch.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                return [call(v0, chunk) for v0 in range(0, V, chunk)]
+
+        ms = timed(lambda: job(default_call), 3)
+        out["default_bf16"] = {"value": V / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                               "what": f"unmodified reference ({os.path.basename(ref)}), pipeline(torch_dtype=bfloat16), ATTN_IMPL={attn}, "
+                                       "allow_tf32: encoder bf16, view transformer fp32/TF32 SDPA (its shipped behaviour)"}
+        if attn == "sdpa":
+            from renderformer.utils.transform import trans_to_cam_coord  # the reference's own helpers
+
+            def fair_call(v0=0, nv=V):
+                # what pipeline.render does (rendering_pipeline.py:60-125) with tf32_view_tf=False, i.e. the view
+                # transformer under bf16 autocast too
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    tex = sc["texture"].clone()
+                    tex[:, :, -3:] = torch.log10(tex[:, :, -3:] + 1.0)
+                    c2w, fov = sc["c2w"][:, v0:v0 + nv], sc["fov"][:, v0:v0 + nv]
+                    B, nv_ = c2w.shape[:2]
+                    tri = sc["triangles"]
+                    tri_cam, c2w_id, _ = trans_to_cam_coord(c2w.reshape(-1, 4, 4), torch.repeat_interleave(tri, nv_, dim=0))
+                    rays_o, rays_d = pipe.ray_generator(c2w_id.reshape(B, nv_, 4, 4), fov / 180.0 * torch.pi, args.resolution)
+                    img = pipe.model(tri.reshape(B, -1, 9), tex, sc["mask"], sc["vn"].reshape(B, -1, 9), rays_o=rays_o,
+                                     rays_d=rays_d, tri_vpos_view_tf=tri_cam.reshape(B, nv_, -1, 9), tf32_view_tf=False)
+                    return torch.pow(10.0, img.permute(0, 1, 3, 4, 2).float()) - 1.0
+            try:
+                ms_f = timed(lambda: job(fair_call), 3)
+                out["fair_bf16"] = {"value": V / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f,
+                                    "what": "unmodified reference model.forward(tf32_view_tf=False) under bf16 autocast "
+                                            "(both transformers bf16), inputs prepared like rendering_pipeline.py:60-101"}
+            except Exception as e:  # noqa: BLE001
+                out["fair_bf16"] = {"unavailable": repr(e)[:300]}
+    except Exception as e:  # noqa: BLE001
+        out["unavailable"] = repr(e)[:300]
+    print("REF_CUDA_JSON " + json.dumps(out), flush=True)
+
+
+def run_ref_cuda(args):
+    res = {}
+    for attn in ("sdpa", "flash_attn"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--ref-cuda-worker", attn, "--config", args.config,
+               "--tris", str(args.tris), "--resolution", str(args.resolution), "--total-views", str(job_views(args, 1))]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("REF_CUDA_JSON ")]
+            res[attn] = json.loads(line[-1][len("REF_CUDA_JSON "):]) if line else {"unavailable": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # noqa: BLE001
+            res[attn] = {"unavailable": repr(e)[:300]}
+    return res
 
 
 # --------------------------------------------------------------------------- clocks
@@ -172,13 +311,15 @@ class ClockSampler:
 # --------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
+    if args.ref_cuda_worker:
+        return ref_cuda_worker(args)
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
     from renderformer_b200 import lib, ops
     from renderformer_b200.config import RenderFormerConfig
-    from renderformer_b200.dist import broadcast_scene_state
+    from renderformer_b200.dist import render_sharded, render_stream_sharded, view_slice
     from renderformer_b200.flops import job_flops, scene_flops, view_flops
     from renderformer_b200.model import RenderFormer, RenderFormerRenderingPipeline
     from renderformer_b200.synth import init_state_dict, make_scene
@@ -198,20 +339,18 @@ def main():
     model.load_state_dict(init_state_dict(cfg, 7))
     pipe = RenderFormerRenderingPipeline(model)
     pipe.to(dev)
-    eng = model.engine()
-    Vl, R, N = args.views_per_gpu, args.resolution, args.tris
-    pipe.view_chunk = args.view_chunk or Vl
+    model.engine()
+    R, N = args.resolution, args.tris
+    V = job_views(args, world)
+    pipe.view_chunk = max(1, args.view_chunk)
     pipe.view_streams = args.view_streams
+    mine = view_slice(V, world, rank)
+    Vl = mine.stop - mine.start
 
-    scene = make_scene(N, Vl * world, seed=0)
+    scene = make_scene(N, V, seed=0)
     host = {k: v.pin_memory() for k, v in scene.items()}
-    my = slice(rank * Vl, (rank + 1) * Vl)
-    host["c2w_local"] = scene["c2w"][:, my].contiguous().pin_memory()
-    host["fov_local"] = scene["fov"][:, my].contiguous().pin_memory()
     d_in = {k: v.to(dev) for k, v in host.items()}
-    out_host = torch.empty((1, Vl, R, R, 3), dtype=torch.float32).pin_memory()
-    gather_list = [torch.empty((1, Vl, R, R, 3), dtype=torch.float32, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
+    out_host = torch.empty((1, V if world == 1 else Vl, R, R, 3), dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -219,41 +358,19 @@ def main():
         torch.cuda.synchronize()
 
     graphs = not args.no_cuda_graphs
-    recv_state = None
 
-    def step_device(inp):
-        """Both stages with inputs resident in HBM; returns this rank's images."""
+    def step_device(inp, dst=0):
+        """The whole job with inputs resident in HBM; the images end up on rank 0 (dst=0)."""
         if world == 1:
-            if pipe.cuda_graphs:  # one CUDA-graph replay of the whole call (inputs copied into its static buffers)
-                return pipe.render(inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w_local"],
-                                   inp["fov_local"], resolution=R, torch_dtype=torch.bfloat16)
-            st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"])
-        else:
-            nonlocal recv_state
-            if rank != 0 and recv_state is None:
-                recv_state = pipe.static_scene_state(1, N)  # persistent receive buffers
-            st = pipe.encode(inp["triangles"], inp["texture"], inp["mask"], inp["vn"]) if rank == 0 else recv_state
-            broadcast_scene_state(st, src=0)  # per-layer triangle K/V + tokens over NVLink (NCCL)
-        img = pipe.render_views(st, inp["c2w_local"], inp["fov_local"], R)
-        if world > 1:
-            dist.gather(img, gather_list, dst=0)
-        return img
+            return pipe.render(inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w"], inp["fov"],
+                               resolution=R, torch_dtype=torch.bfloat16)
+        return render_sharded(pipe, inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w"], inp["fov"],
+                              resolution=R, dst=dst)
 
     def step_e2e():
-        """Public API with HOST buffers: H2D of the step's inputs, render, D2H of the images."""
-        inp = {}
-        if rank == 0 or world == 1:
-            for k in ("triangles", "texture", "mask", "vn"):
-                inp[k] = host[k].to(dev, non_blocking=True)
-        else:
-            inp = {k: None for k in ("triangles", "texture", "mask", "vn")}
-        inp["c2w_local"] = host["c2w_local"].to(dev, non_blocking=True)
-        inp["fov_local"] = host["fov_local"].to(dev, non_blocking=True)
-        if world == 1:
-            img = pipe.render(inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w_local"],
-                              inp["fov_local"], resolution=R, torch_dtype=torch.bfloat16)
-        else:
-            img = step_device(inp)
+        """Public API with HOST buffers, one blocking call per step: H2D of the step's inputs, render, D2H."""
+        inp = {k: host[k].to(dev, non_blocking=True) for k in ("triangles", "texture", "mask", "vn", "c2w", "fov")}
+        img = step_device(inp, dst=None)
         out_host.copy_(img, non_blocking=False)
 
     def timed(fn, steps):
@@ -277,154 +394,143 @@ def main():
     ms_step = timed(lambda: step_device(d_in), args.steps)
     launches = (lib.launch_count() + pipe.replayed_launches - launches0)
     clocks = sampler.stop() if sampler else None
-    frames = Vl * world
-    value = frames / (ms_step * 1e-3)
+    value = V / (ms_step * 1e-3)
+
+    # ---- N > 1 correctness, outside the timed region: the gathered images of the sharded job must be
+    # bit-identical to rank 0's own single-GPU render of the same views
+    sharded_equals_single = None
+    if world > 1:
+        got = step_device(d_in)
+        if rank == 0:
+            got = got.clone()
+            pipe.cuda_graphs = False
+            ref_img = pipe.render(d_in["triangles"], d_in["texture"], d_in["mask"], d_in["vn"], d_in["c2w"], d_in["fov"],
+                                  resolution=R, torch_dtype=torch.bfloat16)
+            sharded_equals_single = bool(torch.equal(got, ref_img))
+            if not sharded_equals_single:
+                print(f"bench: sharded != single, max |d| = {(got - ref_img).abs().max().item():.3e}", file=sys.stderr)
+            del got, ref_img
+            pipe.cuda_graphs = graphs
+        dist.barrier()
 
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
-        h2d = sum(host[k].numel() * host[k].element_size() for k in ("triangles", "texture", "mask", "vn"))
-        h2d += world * (host["c2w_local"].numel() + host["fov_local"].numel()) * 4
-        e2e = {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(world * out_host.numel() * 4),
-               "api": "RenderFormerRenderingPipeline.render, one blocking call per step"}
+        small = sum(host[k].numel() * host[k].element_size() for k in ("triangles", "mask", "vn"))
+        host_scene = {k: host[k] for k in ("triangles", "texture", "mask", "vn", "c2w", "fov")}
         if world == 1:
-            # the batch API (batch_infer.py use case): every step still uploads its own inputs from
-            # pinned host memory and downloads its own images inside the timed region, but the upload
-            # of step i+1 and the download of step i overlap the kernels of the neighbouring step
-            host_scene = {"triangles": host["triangles"], "texture": host["texture"], "mask": host["mask"],
-                          "vn": host["vn"], "c2w": host["c2w_local"], "fov": host["fov_local"]}
-
+            # the batch API (batch_infer.py use case): every step still uploads its own inputs from pinned host
+            # memory and downloads its own images inside the timed region, but the upload of step i+1 and the
+            # download of step i overlap the kernels of the neighbouring step
             def stream_steps(n):
                 sink = 0.0
-                for img in pipe.render_stream((host_scene for _ in range(n)), resolution=R,
-                                              torch_dtype=torch.bfloat16):
+                for img in pipe.render_stream((host_scene for _ in range(n)), resolution=R, torch_dtype=torch.bfloat16):
                     sink += float(img[0, 0, 0, 0, 0])  # touch the host result of every step
                 return sink
-
-            stream_steps(3)
-            ms_stream = timed(lambda: stream_steps(args.steps), 1) / args.steps
-            e2e = {"value": frames / (ms_stream * 1e-3), "unit": UNIT, "ms_per_step": ms_stream,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4),
-                   "api": "RenderFormerRenderingPipeline.render_stream (host scenes in, pinned host images out; "
-                          "copies of neighbouring steps overlap the kernels)",
-                   "single_call": {"value": frames / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
-                                   "api": "RenderFormerRenderingPipeline.render, one blocking call per step"}}
+            api = ("RenderFormerRenderingPipeline.render_stream (host scenes in, pinned host images out; copies of "
+                   "neighbouring steps overlap the kernels)")
+            h2d = small + host["texture"].numel() * 4 + (host["c2w"].numel() + host["fov"].numel()) * 4
         else:
-            from renderformer_b200.dist import render_stream_sharded
-            host_scene = {k: host[k] for k in ("triangles", "texture", "mask", "vn", "c2w", "fov")}
-
             def stream_steps(n):
                 sink = 0.0
                 for _mine, img in render_stream_sharded(pipe, (host_scene for _ in range(n)), resolution=R):
-                    sink += float(img[0, 0, 0, 0, 0])
+                    sink += float(img[0, 0, 0, 0, 0]) if img.numel() else 0.0
                 return sink
-
-            stream_steps(3)
-            ms_stream = timed(lambda: stream_steps(args.steps), 1) / args.steps
-            e2e = {"value": frames / (ms_stream * 1e-3), "unit": UNIT, "ms_per_step": ms_stream,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(world * out_host.numel() * 4),
-                   "api": "renderformer_b200.dist.render_stream_sharded (rank 0 uploads the scene, NCCL broadcast of "
-                          "the scene state, every rank renders and downloads its own views; copies overlap kernels)",
-                   "single_call": {"value": frames / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
-                                   "api": "one blocking step per scene"}}
+            api = ("renderformer_b200.dist.render_stream_sharded (every rank uploads the geometry and its own rows of the "
+                   "texture, row-sharded scene stage, every rank renders and downloads its own views; copies overlap kernels)")
+            # summed over ranks: geometry on every rank, each texture row once, each camera once
+            h2d = world * small + host["texture"].numel() * 4 + (host["c2w"].numel() + host["fov"].numel()) * 4
+        stream_steps(3)
+        ms_stream = timed(lambda: stream_steps(args.steps), 1) / args.steps
+        e2e = {"value": V / (ms_stream * 1e-3), "unit": UNIT, "ms_per_step": ms_stream,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(V * R * R * 3 * 4), "api": api,
+               "single_call": {"value": V / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
+                               "api": "one blocking call per step (full scene uploaded by every rank)" if world > 1 else
+                                      "RenderFormerRenderingPipeline.render, one blocking call per step"}}
 
     roofline = None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
         peak_tf, _, peak_src = load_peaks()
         pipe.cuda_graphs = False  # per-launch events need eager launches
-        ops.PROFILE = []
-        torch.cuda.synchronize()
-        step_device(d_in) if world == 1 else (pipe.render_views(
-            pipe.encode(d_in["triangles"], d_in["texture"], d_in["mask"], d_in["vn"]), d_in["c2w_local"],
-            d_in["fov_local"], R))
+        ops.PROFILE = [] if rank == 0 else None
+        barrier()
+        step_device(d_in, dst=None)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         pipe.cuda_graphs = graphs
-        by = {}
-        for kind, fl, a, b, _tag in prof:
-            t = a.elapsed_time(b) * 1e-3
-            cur = by.setdefault(kind, [0.0, 0.0, 0])
-            cur[0] += fl
-            cur[1] += t
-            cur[2] += 1
-        g = by.get("gemm", [0.0, 1.0, 1])
-        att = by.get("attention", [0.0, 1.0, 1])
-        ach = g[0] / g[1] / 1e12
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01e_gemm_traffic.json")
-        if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, Vl) == (4096, 512, 4):
-            with open(tpath) as f:
-                tj = json.load(f)
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01e_gemm_traffic.json (ncu dram__bytes_read+write, avg over one step's GEMM launches)"
-        roofline = {
-            "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
-            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-            "traffic_source": traffic_src, "flop_per_launch": g[0] / g[2],
-            "peak_source": peak_src, "launches_per_step": g[2], "avg_launch_us": g[1] / g[2] * 1e6,
-            "share_of_step": g[1] * 1e3 / ms_step,
-            "method": "per-launch CUDA events on the launch stream, one instrumented step after the timed region",
-            "attention": {"kernel": "attn_tc_kernel", "achieved": att[0] / att[1] / 1e12, "unit": "TFLOP/s",
-                          "frac": att[0] / att[1] / 1e12 / peak_tf, "launches_per_step": att[2],
-                          "share_of_step": att[1] * 1e3 / ms_step},
-        }
+        if rank == 0:
+            by = {}
+            for kind, fl, a, b, _tag in prof:
+                t = a.elapsed_time(b) * 1e-3
+                cur = by.setdefault(kind, [0.0, 0.0, 0])
+                cur[0] += fl
+                cur[1] += t
+                cur[2] += 1
+            g = by.get("gemm", [0.0, 1.0, 1])
+            att = by.get("attention", [0.0, 1.0, 1])
+            ach = g[0] / g[1] / 1e12
+            traffic, traffic_src = None, None
+            for name in ("r02_gemm_traffic.json", "r01e_gemm_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, pipe.view_chunk) == (4096, 512, 4):
+                    with open(tpath) as f:
+                        tj = json.load(f)
+                    traffic = tj["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{name} (ncu dram__bytes_read+write, avg over the GEMM launches of one scene + 4-view chunk)"
+                    break
+            roofline = {
+                "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_source": traffic_src, "flop_per_launch": g[0] / g[2],
+                "peak_source": peak_src, "launches_per_step": g[2], "avg_launch_us": g[1] / g[2] * 1e6,
+                "share_of_step": g[1] * 1e3 / ms_step,
+                "method": "per-launch CUDA events on the launch stream, one instrumented eager step (rank 0's share of the "
+                          "job) after the timed region",
+                "attention": {"kernel": "attn3_tc_kernel / attn2_tc_kernel / attn_swin_kernel", "achieved": att[0] / att[1] / 1e12,
+                              "unit": "TFLOP/s", "frac": att[0] / att[1] / 1e12 / peak_tf, "launches_per_step": att[2],
+                              "share_of_step": att[1] * 1e3 / ms_step},
+            }
     if world > 1:
         dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, ms, cores, sample = cpu_sample(args.config, 2, 1, N, R, Vl)
-        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        r = cpu_arm(args, min(V, 4), 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
-    torch_cuda = None
-    if rank == 0 and world == 1 and args.torch_cuda:
-        # context only: the reference's algorithm executed by torch's own CUDA kernels (SDPA, cuBLAS,
-        # cuDNN) on this GPU.  The unmodified reference cannot travel to the GPU box (it imports
-        # roma / needs /root/reference), so this is the oracle port under bf16 autocast -- a checker
-        # being timed beside the product, never on the product path.
-        from oracle import renderformer_oracle as orc
-        sd_gpu = {k: v.to(dev) for k, v in init_state_dict(cfg, 7).items()}
-        g_in = {k: v.to(dev) for k, v in scene.items()}
-
-        def torch_step():
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                return orc.render(sd_gpu, cfg, g_in["triangles"], g_in["texture"], g_in["mask"], g_in["vn"],
-                                  g_in["c2w"], g_in["fov"], R, view_chunk=Vl)
-        try:
-            for _ in range(2):
-                torch_step()
-            ms_t = timed(torch_step, max(2, min(args.steps, 5)))
-            torch_cuda = {"value": frames / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t, "kind": "port",
-                          "what": "oracle (functional restatement of the reference) on cuda:0, torch SDPA/cuBLAS/cuDNN "
-                                  "kernels, bf16 autocast, K/V recomputed per view like the reference"}
-        except Exception as e:  # noqa: BLE001
-            torch_cuda = {"unavailable": repr(e)[:200]}
-        del sd_gpu, g_in
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        del d_in
+        pipe._graphs.clear()
         torch.cuda.empty_cache()
+        ref_cuda = run_ref_cuda(args)
 
     if rank == 0:
-        step_tflop = job_flops(cfg, N, R, 1, frames) / 1e12
+        step_tflop = job_flops(cfg, N, R, 1, V) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if args.views_per_gpu > 0 else "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"{args.config} (483M, random-init), synthetic {N}-triangle scene, {R}x{R}, "
-                            f"{Vl} views/GPU per step ({frames} views total; 32-view batch at 8 GPUs = BASELINE configs[2]); "
-                            "scene stage once per step on rank 0 + NCCL broadcast of per-layer K/V",
-                "l2": "inputs + weights (~1.3 GB per step) exceed the 126 MB L2; no explicit flush",
-                "launch": (("one CUDA-graph replay per step" if world == 1 else "CUDA-graph replay of each stage, NCCL eager")
-                           + " (pipeline.cuda_graphs)" if graphs else "eager launches from Python"),
+                "workload": workload_text(args, world),
+                "parallelism": (f"scene stage row-sharded over {world} ranks (one NCCL all-gather of the 16-bit residual stream per "
+                                f"encoder layer), {Vl} views per rank, image gather on rank 0" if world > 1 else "single GPU"),
+                "views_per_decoder_pass": pipe.view_chunk,
+                "l2": "inputs + weights + activations (> 1.3 GB per step) exceed the 126 MB L2; no explicit flush",
+                "launch": ("one CUDA-graph replay per step and rank, NCCL all-gathers inside the graph; image gather eager"
+                           if graphs else "eager launches from Python"),
                 "algorithmic_tflop_per_step": step_tflop,
                 "model_flops_utilisation": step_tflop / (ms_step * 1e-3) / world / load_peaks()[0],
                 "scene_tflop": scene_flops(cfg, N) / 1e12, "view_tflop": view_flops(cfg, N, R) / 1e12,
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "sharded_equals_single": sharded_equals_single,
         }
-        if torch_cuda is not None:
-            line["torch_cuda_port"] = torch_cuda
+        if ref_cuda is not None:
+            line["reference_cuda"] = ref_cuda
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

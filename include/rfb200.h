@@ -167,11 +167,11 @@ int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
 int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* out, int out_dtype, long long ldo,
                 int rows, int d, float eps, const int* gather, rfb_stream_t stream);
 
-/* out16[r,:] = cast(x[r,:]) (16-bit), sumsq[r*sumsq_ld] = sum(x[r,:]^2), sumsq[r*sumsq_ld + 1..parts) = 0:
+/* out16[r*ld16 + :] = cast(x[r,:]) (16-bit), sumsq[r*sumsq_ld] = sum(x[r,:]^2), sumsq[r*sumsq_ld + 1..parts) = 0:
  * seeds the fused-norm GEMM chain (the input side of nn.RMSNorm, layers/attention.py:503-526,
  * without materialising norm(x)) in the partial-sum layout rfb_gemm's out_sumsq uses. */
-int rfb_rowstat(const float* x, void* out16, int out_dtype, float* sumsq, int sumsq_ld, int parts, int rows, int d,
-                rfb_stream_t stream);
+int rfb_rowstat(const float* x, void* out16, int out_dtype, long long ld16, float* sumsq, int sumsq_ld, int parts,
+                int rows, int d, rfb_stream_t stream);
 
 /* QK-RMSNorm over the full model width + triangle RoPE (layers/attention.py:128-141,
  * encodings/rope.py:78-149,152-206): fp32 [rows, nseg*d] -> bf16.  Input row = r % in_period

@@ -11,56 +11,21 @@ manifest, so the committed vectors pin both the oracle and the CUDA path.
 import json
 import os
 import sys
-import types
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("RFB_REFERENCE", "/root/reference")
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+os.environ.setdefault("RFB_REFERENCE", "/root/reference")  # golden vectors come from the read-only mount itself
+REF = os.environ["RFB_REFERENCE"]
 os.environ["ATTN_IMPL"] = "sdpa"
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 
-def _install_roma_stub():
-    class Rigid:
-        def __init__(self, linear, translation):
-            self.linear, self.translation = linear, translation
-
-        @staticmethod
-        def from_homogeneous(M):
-            return Rigid(M[..., :3, :3], M[..., :3, 3])
-
-        def inverse(self):
-            Rt = self.linear.transpose(-1, -2)
-            return Rigid(Rt, -(Rt @ self.translation[..., None])[..., 0])
-
-        def __getitem__(self, idx):
-            return Rigid(self.linear[idx], self.translation[idx])
-
-        def linear_apply(self, v):
-            return (self.linear @ v[..., None])[..., 0]
-
-        def apply(self, v):
-            return self.linear_apply(v) + self.translation
-
-    m = types.ModuleType("roma")
-    m.Rigid = Rigid
-    sys.modules["roma"] = m
-
-
 def load_reference():
-    """Import the reference package from REF, making sure the repo's own drop-in shim of the
-    same name is not picked up."""
-    _install_roma_stub()
-    sys.path = [REF] + [p for p in sys.path if os.path.abspath(p or ".") != REPO]
-    for k in [k for k in sys.modules if k == "renderformer" or k.startswith("renderformer.")]:
-        del sys.modules[k]
-    import renderformer  # noqa: F401  (reference)
-    assert os.path.abspath(renderformer.__file__).startswith(REF), renderformer.__file__
-    from renderformer.models.config import RenderFormerConfig as RefConfig
-    from renderformer.models.renderformer import RenderFormer as RefModel
-    from renderformer.pipelines.rendering_pipeline import RenderFormerRenderingPipeline as RefPipe
-    sys.path.append(REPO)
+    from oracle.reference_loader import load_reference as _load
+    RefConfig, RefModel, RefPipe, _ = _load("sdpa")
     return RefConfig, RefModel, RefPipe
 
 
@@ -73,7 +38,29 @@ CASES = [
     ("large_small", "v1_1_swin_large", 256, None, 1, 128, 3, 7),
     ("base_small", "v1_base", 256, 272, 1, 64, 4, 7),
     ("large_4096_512", "v1_1_swin_large", 4096, None, 1, 512, 0, 7),
+    # every configuration a throughput number is quoted on: the 4-view batch of the
+    # metric, BASELINE configs[1] (cbox, 5633 triangles), a 1024^2 frame (16384 ray tokens), an 8192-triangle
+    # scene, and a two-scene batch.  Big frames are stored pixel-subsampled (`hdr_stride`).
+    ("large_4096_512_v4", "v1_1_swin_large", 4096, None, 4, 512, 0, 7),
+    ("large_cbox_512", "v1_1_swin_large", "cbox", None, 1, 512, 0, 7),
+    ("large_1024_1024", "v1_1_swin_large", 1024, None, 1, 1024, 5, 7),
+    ("large_8192_256", "v1_1_swin_large", 8192, None, 1, 256, 6, 7),
+    ("large_b2", "v1_1_swin_large", 192, 208, 2, 128, 8, 7),
 ]
+EXTRA = {  # name -> (number of scenes in the batch, pixel stride of the stored image)
+    "large_4096_512_v4": (1, 2), "large_cbox_512": (1, 1), "large_1024_1024": (1, 4), "large_8192_256": (1, 1),
+    "large_b2": (2, 1),
+}
+
+
+def build_scene(n_tris, views, scene_seed, pad_to, batch=1):
+    """Host tensors of a golden case: synthetic scene(s) or the converted examples/cbox.json fixture."""
+    from renderformer_b200.synth import make_scene
+    if n_tris == "cbox":
+        from renderformer_b200 import scene_io as sio
+        return sio.to_pipeline_inputs(sio.load_npz(os.path.join(REPO, "tests", "golden", "cbox_scene.npz")))
+    scenes = [make_scene(n_tris, views, seed=scene_seed + b, pad_to=pad_to) for b in range(batch)]
+    return {k: torch.cat([sc[k] for sc in scenes], dim=0) for k in scenes[0]}
 
 
 def main():
@@ -112,7 +99,9 @@ def main():
         missing = model.load_state_dict(sd, strict=True)
         model.eval()
         pipe = RefPipe(model)
-        scene = make_scene(n_tris, views, seed=scene_seed, pad_to=pad_to)
+        batch, hdr_stride = EXTRA.get(name, (1, 1))
+        scene = build_scene(n_tris, views, scene_seed, pad_to, batch)
+        n_real = scene["triangles"].shape[1] if n_tris == "cbox" else n_tris
 
         taps_ref = {}
         hooks = [model.transformer.register_forward_hook(lambda m, i, o: taps_ref.__setitem__("seq", o.detach().clone()))]
@@ -129,16 +118,16 @@ def main():
         rng = (ref_img.min().item(), ref_img.max().item())
         print(f"{name}: oracle-vs-reference max|d| image {d_img:.3e} (range {rng[0]:.4f}..{rng[1]:.4f}) seq {d_seq:.3e}")
         assert d_img <= 2e-4 * max(1.0, abs(rng[1])), "oracle restatement disagrees with the reference"
-        big = n_tris >= 1024  # keep the full-size fixture small: image + every 16th seq row as fp16
+        big = n_real >= 1024  # keep the full-size fixture small: image + every 16th seq row as fp16
         np.savez_compressed(
             os.path.join(out_dir, f"{name}.npz"),
-            hdr=ref_img.float().numpy(),
+            hdr=ref_img.float().numpy()[:, :, ::hdr_stride, ::hdr_stride],
             seq=(taps_ref["seq"][:, ::16].numpy().astype(np.float16) if big else taps_ref["seq"].numpy()),
             dec_last=np.zeros(1, np.float32) if big else taps["dec_feats"][-1].float().numpy())
-        manifest["cases"][name] = dict(config=cfg_name, n_tris=n_tris, pad_to=pad_to, views=views, resolution=res,
+        manifest["cases"][name] = dict(config=cfg_name, n_tris=n_real, scene="cbox" if n_tris == "cbox" else "synthetic", pad_to=pad_to, views=views, resolution=res,
                                        scene_seed=scene_seed, weight_seed=wseed, oracle_vs_ref_img=d_img,
                                        oracle_vs_ref_seq=d_seq, hdr_min=rng[0], hdr_max=rng[1],
-                                       seq_row_stride=16 if big else 1)
+                                       seq_row_stride=16 if big else 1, batch=batch, hdr_stride=hdr_stride)
     with open(os.path.join(out_dir, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
     print("wrote", out_dir)

@@ -439,7 +439,8 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
   p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
 
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flags;
+  bool& attr_set = attr_flags.get();
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
         cudaSuccess)

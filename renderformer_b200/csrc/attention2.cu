@@ -350,7 +350,8 @@ int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   p.q_sumsq = a->q_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
   p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flags;
+  bool& attr_set = attr_flags.get();
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=
         cudaSuccess)

@@ -340,7 +340,8 @@ int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_
   p.q_sumsq = a->q_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
   p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flags;
+  bool& attr_set = attr_flags.get();
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3Smem) != cudaSuccess)
       return RFB_ERR_LAUNCH;

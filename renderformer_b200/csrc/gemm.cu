@@ -773,7 +773,8 @@ template <int BN, int EK = EK_GENERIC>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                        int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flags;
+  bool& attr_set = attr_flags.get();
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmemBytes) != cudaSuccess)
@@ -984,7 +985,8 @@ template <int BN, int EK = EK_GENERIC>
 static int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
                             cudaStream_t stream) {
   using Cfg = HaloCfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flags;
+  bool& attr_set = attr_flags.get();
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_halo_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmemBytes) != cudaSuccess)

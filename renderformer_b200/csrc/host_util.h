@@ -72,15 +72,27 @@ inline int check_launch(const char* what) {
   return RFB_OK;
 }
 
+// Launch-side caches are kept PER DEVICE: one process may drive several GPUs (a model on cuda:1 while
+// cuda:0 is current elsewhere), and cudaFuncSetAttribute / the SM count belong to the device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+struct PerDeviceFlag {
+  bool v[kMaxDevices] = {};
+  bool& get() { return v[current_device()]; }
+};
+
 inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace rfb

@@ -71,7 +71,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, long long ldx, const
 // Row statistics for the fused-norm GEMMs: out16[r,:] = cast(x[r,:]), sumsq[r] = sum(x[r,:]^2).
 // (Seeds the (16-bit copy, sum of squares) pair that the residual GEMM epilogues then maintain.)
 // ---------------------------------------------------------------------------------------------
-__global__ void rowstat_kernel(const float* __restrict__ x, void* __restrict__ out16, int out_dtype,
+__global__ void rowstat_kernel(const float* __restrict__ x, void* __restrict__ out16, int out_dtype, long long ld16,
                                float* __restrict__ sumsq, int sumsq_ld, int parts, int rows, int d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -84,7 +84,7 @@ __global__ void rowstat_kernel(const float* __restrict__ x, void* __restrict__ o
     if (j < nvec) {
       const float4 v = xr[j * 32 + lane];
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      store4_16(out16, out_dtype, (long long)row * d + (j * 32 + lane) * 4, v.x, v.y, v.z, v.w);
+      store4_16(out16, out_dtype, (long long)row * ld16 + (j * 32 + lane) * 4, v.x, v.y, v.z, v.w);
     }
   ss = warp_sum(ss);
   if (lane < parts) sumsq[(long long)row * sumsq_ld + lane] = lane == 0 ? ss : 0.f;
@@ -501,12 +501,12 @@ extern "C" int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* 
   RFB_LAUNCHED("rmsnorm_kernel");
 }
 
-extern "C" int rfb_rowstat(const float* x, void* out16, int out_dtype, float* sumsq, int sumsq_ld, int parts,
-                           int rows, int d, rfb_stream_t stream) {
-  if (!x || !out16 || !sumsq || rows <= 0 || d % 128 || d > kMaxVec * 128) return RFB_ERR_ARG;
+extern "C" int rfb_rowstat(const float* x, void* out16, int out_dtype, long long ld16, float* sumsq, int sumsq_ld,
+                           int parts, int rows, int d, rfb_stream_t stream) {
+  if (!x || !out16 || !sumsq || rows <= 0 || d % 128 || d > kMaxVec * 128 || ld16 < d || ld16 % 4) return RFB_ERR_ARG;
   if (parts < 1 || parts > 32 || sumsq_ld < parts) return RFB_ERR_ARG;
   const int wpb = 8;
-  rowstat_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(x, out16, out_dtype, sumsq, sumsq_ld, parts, rows, d);
+  rowstat_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(x, out16, out_dtype, ld16, sumsq, sumsq_ld, parts, rows, d);
   RFB_LAUNCHED("rowstat_kernel");
 }
 

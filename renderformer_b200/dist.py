@@ -1,8 +1,18 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
 
-The path shards over views: the view-independent stage runs once per scene on
-`src`, its output -- encoder tokens plus the hoisted per-layer decoder K (pre-RoPE) and V^T --
-is broadcast, every rank renders a contiguous slice of the views, images are gathered."""
+Both stages shard:
+
+* view-independent stage -- the token ROWS of the triangle sequence are split over the ranks
+  (`row_shard` -> engine.RowShard): every rank constructs, attends and feeds forward its own rows and
+  one all-gather per encoder layer exchanges the 16-bit copy of the residual stream (8.6 MB for 4096
+  triangles) that the next layer's K / V projection needs of all rows.  No rank waits for "the
+  encoder rank", no 300 MB K/V broadcast: the hoisted decoder K / V are recomputed from the gathered
+  stream on every rank (0.2 TFLOP).
+* view-dependent stage -- every rank renders a contiguous slice of the views (`view_slice`); the
+  only collective is the final image gather.
+
+`broadcast_scene_state` (rank `src` encodes alone, its state is broadcast -- the north_star's
+wording) is kept for callers that hold the scene on one rank only."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -10,7 +20,13 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
-from .engine import SceneState
+from .engine import RowShard, SceneState
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
 
 
 def view_slice(n_views: int, world: int, rank: int) -> slice:
@@ -20,9 +36,28 @@ def view_slice(n_views: int, world: int, rank: int) -> slice:
     return slice(start, start + base + (1 if rank < extra else 0))
 
 
+def all_gather_rows(full: torch.Tensor, chunk: torch.Tensor, group=None) -> None:
+    """full [world*S, ...] <- every rank's chunk [S, ...]; `chunk` may be (and in the engine is) the
+    rank's own slice of `full` (in-place all-gather, no staging copy with NCCL)."""
+    if full.is_cuda:
+        dist.all_gather_into_tensor(full, chunk, group=group)
+    else:  # gloo (CPU tests): no aliasing between input and outputs
+        world = dist.get_world_size(group)
+        s = chunk.shape[0]
+        dist.all_gather([full[r * s:(r + 1) * s] for r in range(world)], chunk.clone(), group=group)
+
+
+def row_shard(group=None) -> Optional[RowShard]:
+    """RowShard of the current process group (None when there is one rank)."""
+    world, rank = _world()
+    if world == 1:
+        return None
+    return RowShard(rank, world, lambda full, chunk: all_gather_rows(full, chunk, group))
+
+
 def broadcast_scene_state(state: SceneState, src: int = 0) -> SceneState:
     """In-place broadcast of every tensor of a SceneState (receivers pass alloc_scene_state())."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if _world()[0] > 1:
         for t in state.tensors():
             dist.broadcast(t, src=src)
     return state
@@ -31,9 +66,9 @@ def broadcast_scene_state(state: SceneState, src: int = 0) -> SceneState:
 def gather_images(img: torch.Tensor, dst: int = 0, sizes: Optional[List[int]] = None):
     """Gather per-rank image stacks [V_r, H, W, 3] on `dst` (returns the concatenation there, None
     elsewhere).  `sizes` lists V_r per rank when the split is uneven."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    world, rank = _world()
+    if world == 1:
         return img
-    world, rank = dist.get_world_size(), dist.get_rank()
     if sizes is None:
         sizes = [img.shape[0]] * world
     vmax = max(sizes)
@@ -48,49 +83,98 @@ def gather_images(img: torch.Tensor, dst: int = 0, sizes: Optional[List[int]] = 
 
 
 @torch.no_grad()
-def render_stream_sharded(pipe, scenes, resolution: int = 512, src: int = 0, ldr: Optional[str] = None):
+def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int = 512, dst: Optional[int] = 0,
+                   texture_own_rows: bool = False):
+    """`RenderFormerRenderingPipeline.render` on all ranks of the process group: every rank passes the
+    SAME scene and the full camera list c2w [B,V,4,4] / fov [B,V,1]; the scene stage is row-sharded, each
+    rank renders `view_slice(V)`, and the images are gathered on `dst` (returns [B,V,H,W,3] there and
+    None elsewhere; `dst=None` skips the gather and returns this rank's [B,V_rank,H,W,3]).  With
+    `pipe.cuda_graphs` and device inputs the whole per-rank schedule, NCCL all-gathers included, is one
+    CUDA-graph replay."""
+    world, rank = _world()
+    V = c2w.shape[1]
+    mine = view_slice(V, world, rank)
+    c2w_l, fov_l = c2w[:, mine].contiguous(), fov[:, mine].contiguous()
+    sh = row_shard()
+    if world == 1:
+        img = pipe.render(triangles, texture, mask, vn, c2w_l, fov_l, resolution=resolution)
+    else:
+        eng = pipe.model.engine()
+        inputs = (triangles, texture, mask, vn, c2w_l, fov_l)
+
+        def run(tri, tex, msk, vnn, cw, fv):
+            st = eng.encode_scene(tri, tex, msk, vnn, shard=sh, texture_own_rows=texture_own_rows)
+            return pipe.render_views(st, cw, fv, resolution, _eager=True)
+        if pipe.cuda_graphs and all(t.is_cuda for t in inputs) and mine.stop > mine.start:
+            key = ("render_sharded", id(eng), rank, world, resolution, pipe.view_chunk, texture_own_rows) + pipe._sig(inputs)
+            img = pipe._graph_entry(key, inputs, run)
+        else:
+            img = run(*inputs)
+    if dst is None or world == 1:
+        return img
+    sizes = [view_slice(V, world, r).stop - view_slice(V, world, r).start for r in range(world)]
+    B = img.shape[0]
+    out = gather_images(img.transpose(0, 1).contiguous() if B > 1 else img[0], dst=dst, sizes=sizes)
+    if out is None:
+        return None
+    return out.transpose(0, 1).contiguous() if B > 1 else out[None]
+
+
+@torch.no_grad()
+def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str] = None):
     """Multi-GPU counterpart of `RenderFormerRenderingPipeline.render_stream`: every rank iterates the SAME
-    sequence of host scene dicts (keys of `render`); rank `src` uploads geometry + texture and runs the
-    view-independent stage, its SceneState is broadcast with NCCL, each rank renders its contiguous slice
-    of the views and downloads its own images (no gather: a rank can write its own frames).  Uploads of
-    scene i+1 and downloads of scene i overlap the kernels of the neighbouring scene.
+    sequence of host scene dicts (keys of `render`).  Each rank uploads the geometry and only ITS OWN
+    rows of the texture (1/world of the 218 MB), the scene stage runs row-sharded, each rank renders its
+    contiguous slice of the views and downloads its own images (no gather: a rank can write its own
+    frames).  Uploads of scene i+1 and downloads of scene i overlap the kernels of the neighbouring scene.
 
     Yields (view_slice, pinned host tensor [B, V_rank, H, W, 3]) per scene; the buffer belongs to a ring of
     three."""
     dev = pipe.device
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-    rank = dist.get_rank() if world > 1 else 0
+    world, rank = _world()
     main = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(dev)
+    eng = pipe.model.engine()
+    sh = row_shard()
 
     def upload(sc):
         V = sc["c2w"].shape[1]
         mine = view_slice(V, world, rank)
+        N = sc["triangles"].shape[1]
+        t0, t1 = eng.own_triangles(N, sh) if sh is not None else (0, N)
         with torch.cuda.stream(copy):
             d = {"c2w": sc["c2w"][:, mine].contiguous().to(dev, non_blocking=True),
                  "fov": sc["fov"][:, mine].contiguous().to(dev, non_blocking=True)}
-            if rank == src:
-                for k in ("triangles", "texture", "mask", "vn"):
-                    d[k] = sc[k].to(dev, non_blocking=True)
+            for k in ("triangles", "mask", "vn"):
+                d[k] = sc[k].to(dev, non_blocking=True)
+            d["texture"] = sc["texture"][:, t0:t1].to(dev, non_blocking=True)  # contiguous for one scene per batch
             ev = torch.cuda.Event()
             ev.record(copy)
-        return d, ev, mine, tuple(sc["triangles"].shape[:2])
+        return d, ev, mine
 
     it = iter(scenes)
     first = next(it, None)
     pending = upload(first) if first is not None else None
     ring, slot, prev = [None, None, None], 0, None
     while pending is not None:
-        d, ev, mine, (B, N) = pending
+        d, ev, mine = pending
         nxt = next(it, None)
         pending = upload(nxt) if nxt is not None else None
         main.wait_event(ev)
-        if rank == src:
-            st = pipe.encode(d["triangles"], d["texture"], d["mask"], d["vn"])
+        if sh is None:
+            img = pipe.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"], resolution=resolution)
         else:
-            st = pipe.static_scene_state(B, N)  # one persistent receive buffer per shape
-        broadcast_scene_state(st, src=src)
-        img = pipe.render_views(st, d["c2w"], d["fov"], resolution)
+            # full camera list is not needed here: the slice was taken on the host
+            inputs = (d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"])
+
+            def run(tri, tex, msk, vnn, cw, fv):
+                st = eng.encode_scene(tri, tex, msk, vnn, shard=sh, texture_own_rows=True)
+                return pipe.render_views(st, cw, fv, resolution, _eager=True)
+            if pipe.cuda_graphs and mine.stop > mine.start:
+                key = ("stream_sharded", id(eng), rank, world, resolution, pipe.view_chunk) + pipe._sig(inputs)
+                img = pipe._graph_entry(key, inputs, run)
+            else:
+                img = run(*inputs)
         for t in d.values():
             t.record_stream(main)
         if ldr is not None:

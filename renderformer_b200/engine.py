@@ -15,7 +15,7 @@ fp16 operands in the token encoders and the DPT head, fp32 accumulation / softma
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Callable, Dict, List, Optional
 
 import torch
 
@@ -57,6 +57,30 @@ class SceneState:
 
     def tensors(self):
         return [self.seq, self.tri, self.mask_u8, self.mask_bits, self.k_all, self.v_all]
+
+
+@dataclass
+class RowShard:
+    """Partition of the triangle-token rows of the view-independent stage over `world` ranks.
+
+    Rank r owns the contiguous rows [r*S, (r+1)*S) of the (padded) token sequence, S = shard_rows().
+    Everything that is row-local (token construction, attention queries, out-projection, SwiGLU) runs
+    on the own rows only; what every rank needs of the others -- the 16-bit copy of the residual stream
+    and its row sums of squares, i.e. the input of the next layer's K / V projection -- is exchanged
+    with ONE all-gather per layer: `all_gather(full, chunk)` fills `full` ([world*S, ld] contiguous)
+    from every rank's `chunk` (= full[rank*S:(rank+1)*S], written in place).  The reference has no
+    counterpart (single device, models/renderformer.py:171-206); SURVEY §8(e) derives the scheme."""
+    rank: int
+    world: int
+    all_gather: Callable[[torch.Tensor, torch.Tensor], None]
+
+    def shard_rows(self, ntp: int) -> int:
+        return _rup(-(-ntp // self.world), 8)
+
+    def my_rows(self, ntp: int):
+        s = self.shard_rows(ntp)
+        r0 = min(self.rank * s, ntp)
+        return r0, min(r0 + s, ntp)
 
 
 def swin_window_maps(Hp: int, Wp: int, shift: int, ws: int = 8):
@@ -213,8 +237,22 @@ class Engine:
 
     # ------------------------------------------------------------------ stage 1
     @torch.no_grad()
-    def encode_scene(self, triangles, texture, mask, vn, texture_is_log: bool = False) -> SceneState:
+    def encode_scene(self, triangles, texture, mask, vn, texture_is_log: bool = False,
+                     shard: Optional[RowShard] = None, texture_own_rows: bool = False,
+                     taps: Optional[dict] = None) -> SceneState:
+        """View-independent stage.  With `shard` (multi-GPU) every rank passes the same scene and runs
+        the row-sharded schedule `_encode_scene_sharded`; every rank returns the complete SceneState.
+        `texture_own_rows`: `texture` holds only the triangles of this rank's rows
+        (`own_triangles(N, shard)`), so a rank never has to upload the other ranks' texels."""
         cfg, w, dev = self.cfg, self.w, self.device
+        if shard is not None and shard.world > 1:
+            B = triangles.shape[0]
+            sts = [self._encode_scene_sharded(triangles[b:b + 1], texture[b:b + 1], mask[b:b + 1], vn[b:b + 1],
+                                              texture_is_log, shard, texture_own_rows) for b in range(B)]
+            if B == 1:
+                return sts[0]
+            cat = [torch.cat(ts, dim=0) for ts in zip(*(st.tensors() for st in sts))]
+            return SceneState(B, sts[0].N, sts[0].Nt, sts[0].Ntp, *cat, sts[0].dv)
         B, N = triangles.shape[:2]
         d, H = cfg.latent_dim, cfg.num_heads
         nreg = cfg.num_register_tokens
@@ -251,9 +289,9 @@ class Engine:
         words = 4 * ((Ntp + 127) // 128)
         bits = ops.pack_mask(mask_u8, self._e((B, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=B)
 
-        return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8)
+        return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8, taps)
 
-    def _encode_fused(self, x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8) -> SceneState:
+    def _encode_fused(self, x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8, taps=None) -> SceneState:
         """Encoder + K/V hoist with RMSNorm fused into the GEMMs.  State carried between GEMMs:
         x (fp32 residual), xb (bf16 copy of x), xsq (per-row partial sums of squares of x, one per
         128 columns)."""
@@ -266,6 +304,8 @@ class Engine:
         xb, xsq = self._e((rows, d), bf), self._e((rows, P), f32)
         xb2, xsq2 = self._e((rows, d), bf), self._e((rows, P), f32)
         ops.rowstat(x, xb, xsq, rows=rows, d=d)
+        if taps is not None:  # per-layer (16-bit stream, row sums) snapshots: what the sharded schedule all-gathers
+            taps.setdefault("enc_stream", []).append((xb.clone(), xsq.clone()))
         for i in range(cfg.num_layers):
             o = f"enc{i}."
             vt = self._e((B, d, Ntp), bf)
@@ -280,6 +320,8 @@ class Engine:
             ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2)
             g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
             ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
+            if taps is not None:
+                taps["enc_stream"].append((xb.clone(), xsq.clone()))
         # hoisted decoder K / V projections of the triangle tokens for ALL layers in two GEMMs
         # (view independent; every layer's kv_norm weight is folded into its rows)
         Lv = cfg.view_transformer_n_layers
@@ -287,6 +329,111 @@ class Engine:
         k_all = ops.gemm(xb, w["dec.wkv_all"], out=self._e((rows, Lv * dv), f32), in_sumsq=xsq, vt_out=v_all,
                          vt_split=Lv * dv, vt_rows_per_batch=Ntp, **nrm).view(B, Ntp, Lv * dv)
         return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_all, v_all, dv)
+
+    def own_triangles(self, N: int, sh: RowShard):
+        """[t0, t1): the triangles whose token rows rank `sh.rank` owns."""
+        nreg = self.cfg.num_register_tokens
+        r0, r1 = sh.my_rows(_rup(N + nreg, 8))
+        return min(max(r0 - nreg, 0), N), min(max(r1 - nreg, 0), N)
+
+    def _encode_scene_sharded(self, triangles, texture, mask, vn, texture_is_log, sh: RowShard,
+                              texture_own_rows: bool = False) -> SceneState:
+        """One scene, token rows split over the ranks of `sh` (see RowShard).  Per layer and rank:
+        [q|k|v] projection of ALL rows from the gathered 16-bit stream (K and V are needed for every
+        key; 26 GFLOP, replicated), QK-norm + RoPE, attention of the OWN query rows against all keys,
+        out-projection + SwiGLU on the own rows, then one all-gather of the own rows' 16-bit copy and
+        row sums of squares.  Row r of the gathered buffer is [d bf16 | d/128 fp32 partial sums | pad],
+        so a single collective moves both.  The arithmetic of a row does not depend on which rank owns
+        it: the result is bit-identical to the single-GPU schedule (tests/test_dist_gpu.py)."""
+        cfg, w, dev = self.cfg, self.w, self.device
+        N = triangles.shape[1]
+        d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
+        nreg = cfg.num_register_tokens
+        Nt, Ntp = N + nreg, _rup(N + nreg, 8)
+        bf, f32, hf = torch.bfloat16, torch.float32, torch.float16
+        S = sh.shard_rows(Ntp)
+        r0, r1 = sh.my_rows(Ntp)
+        rows = r1 - r0
+        P = d // 128
+        ldx = _rup(d + 2 * P, 8)                       # bf16 elements per gathered row
+        tri = triangles.reshape(1, N, 9).to(dev, f32).contiguous()
+        vn9 = vn.reshape(1, N, 9).to(dev, f32).contiguous()
+        mask_u8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8)
+        C_, Pt = cfg.texture_channels, cfg.texture_encode_patch_size
+        const_tex = texture.dim() == 3
+        log_ch = 0 if (cfg.use_ldr or texture_is_log) else 3
+
+        # ---- token construction of the own rows (models/renderformer.py:126-169)
+        t0, t1 = self.own_triangles(N, sh)                          # own triangles
+        nt = t1 - t0
+        p_own = max(0, min(r1, nreg) - r0)                          # register-token rows inside the own range
+        x = self._e((max(rows, 1), d), f32)
+        if rows > 0:
+            if nt > 0:
+                tex = (texture[0] if texture_own_rows else texture[0, t0:t1]).to(dev, f32).contiguous()
+                if tex.shape[0] != nt:
+                    raise ValueError(f"texture holds {tex.shape[0]} triangles, this rank owns {nt}")
+                if const_tex:
+                    if tex.shape[1] != C_:
+                        raise ValueError(f"constant texture must be [B, N, {C_}], got {tuple(texture.shape)}")
+                    tex16 = ops.texture_const_prep(tex, self._e((nt, self.texc_ld), hf), n_tris=nt, channels=C_,
+                                                   ld=self.texc_ld, log_channels=log_ch)
+                    tex_lin = ops.gemm(tex16, w["tex.wr"], bias=w["tex.b"], out_dtype=f32)
+                else:
+                    tex16 = ops.texture_prep(tex, self._e((nt, C_ * Pt * Pt), hf), n_tris=nt, channels=C_,
+                                             texels=Pt * Pt, log_channels=log_ch)
+                    tex_lin = ops.gemm(tex16, w["tex.w"], bias=w["tex.b"], out_dtype=f32)
+                del tex16, tex
+                vn16 = ops.vn_encode(vn9[0, t0:t1], self._e((nt, self.vn_ld), hf), n=nt, nfreq=cfg.vn_pe_num_freqs,
+                                     ld=self.vn_ld)
+                vn_lin = ops.gemm(vn16, w["vn.w"], bias=w["vn.b"], out_dtype=f32)
+            else:
+                tex_lin = vn_lin = w["tri_token"]  # never dereferenced (rows_in = 0)
+            ops.token_assemble(tex_lin, w["tex.norm"], vn_lin, w["vn.norm"], w["tri_token"],
+                               w["reg_tokens"][r0:] if p_own > 0 else None, x, n_prefix=p_own, rows_in=nt,
+                               rows_out=rows, batch=1, d=d)
+        pos = ops.positions(tri[0], mask_u8[0], None, self._e((Ntp, 9), f32), n=N, n_reg=nreg, rows_out=Ntp, n_views=1)
+        words = 4 * ((Ntp + 127) // 128)
+        bits = ops.pack_mask(mask_u8, self._e((1, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=1)
+
+        # ---- gathered 16-bit stream + row sums of squares
+        xbs = self._e((sh.world * S, ldx), bf)
+        xbs32 = xbs.view(f32)                                        # [world*S, ldx/2]
+        xb_all, xsq_all = xbs[:Ntp, :d], xbs32[:Ntp, d // 2:d // 2 + P]
+        xb_own, xsq_own = xbs[r0:r1, :d], xbs32[r0:r1, d // 2:d // 2 + P]
+        chunk = xbs[sh.rank * S:(sh.rank + 1) * S]
+        nrm = dict(norm_dim=d, norm_eps=EPS)
+        if rows > 0:
+            ops.rowstat(x, xb_own, xsq_own, rows=rows, d=d)
+            xb2, xsq2 = self._e((rows, d), bf), self._e((rows, P), f32)
+            att = self._e((rows, d), bf)
+        sh.all_gather(xbs, chunk)
+        for i in range(cfg.num_layers):
+            o = f"enc{i}."
+            vt = self._e((1, d, Ntp), bf)
+            qk = ops.gemm(xb_all, w[o + "wqkv"], out=self._e((Ntp, 2 * d), f32), in_sumsq=xsq_all, vt_out=vt,
+                          vt_split=2 * d, vt_rows_per_batch=Ntp, **nrm)
+            qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((Ntp, 2 * d), bf), rows=Ntp, d=d, nseg=2,
+                                  ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
+            if rows > 0:
+                ops.attention(qkr[r0:r1], qkr[:, d:], vt, att, B=1, H=H, Nq=rows, Nk=Ntp, ldq=2 * d, ldk=2 * d,
+                              ldvt=Ntp, ldo=d, mask_bits=bits, mask_bs=words)
+                ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2, M=rows)
+                g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
+                ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq_own, out16=xb_own, M=rows)
+            sh.all_gather(xbs, chunk)
+        # hoisted decoder K / V of ALL layers from the gathered stream, replicated on every rank (0.2 TFLOP:
+        # cheaper than moving the 300 MB result over NVLink)
+        Lv = cfg.view_transformer_n_layers
+        v_all = self._e((1, Lv * dv, Ntp), bf)
+        k_all = ops.gemm(xb_all, w["dec.wkv_all"], out=self._e((Ntp, Lv * dv), f32), in_sumsq=xsq_all, vt_out=v_all,
+                         vt_split=Lv * dv, vt_rows_per_batch=Ntp, **nrm).view(1, Ntp, Lv * dv)
+        # the fp32 token sequence itself (API completeness / tests): one more gather
+        seq = self._e((sh.world * S, d), f32)
+        if rows > 0:
+            seq[r0:r1].copy_(x[:rows])
+        sh.all_gather(seq, seq[sh.rank * S:(sh.rank + 1) * S])
+        return SceneState(1, N, Nt, Ntp, seq[:Ntp].view(1, Ntp, d), tri, mask_u8, bits, k_all, v_all, dv)
 
     def alloc_scene_state(self, B: int, N: int) -> SceneState:
         """Uninitialised SceneState of the right shapes (receive buffers for the NCCL broadcast)."""

@@ -90,7 +90,7 @@ def load() -> C.CDLL:
         "rfb_gemm": [C.POINTER(GemmArgs), p],
         "rfb_attention": [C.POINTER(AttnArgs), p],
         "rfb_rmsnorm": [p, ll, p, p, i, ll, i, i, f, p, p],
-        "rfb_rowstat": [p, p, i, p, i, i, i, i, p],
+        "rfb_rowstat": [p, p, i, ll, p, i, i, i, i, p],
         "rfb_qknorm_rope": [p, ll, i, p, p, ll, i, i, i, f, p, p, i, p],
         "rfb_token_assemble": [p, p, p, p, p, p, i, p, i, i, i, i, p],
         "rfb_texture_prep": [p, p, ll, i, i, i, p],

@@ -94,11 +94,16 @@ class RenderFormer(_Params):
         """Reference signature and semantics (models/renderformer.py:171-206): tri_vpos_list [B,N,9],
         texture_patch_list [B,N,13,P,P] with the emission channels ALREADY log-encoded (the pipeline does
         that before calling the model, rendering_pipeline.py:67-68), valid_mask [B,N], vns [B,N,9],
-        rays_o [B,V,3] (unused: the origin is 0 in camera space), rays_d [B,V,H,W,3] camera-space ray
+        rays_o [B,V,3] (must be 0: the origin of camera-space rays; anything else raises), rays_d [B,V,H,W,3] camera-space ray
         map, tri_vpos_view_tf [B,V,N,9] camera-space vertices.  Returns log-encoded images
         [B, V, 3, H, W] like the reference.  Alternatively pass cameras as keywords (`c2w` [B,V,4,4],
-        `fov` [B,V,1] degrees, `resolution`) and leave rays_d / tri_vpos_view_tf None.  The pipeline
-        calls the engine directly and skips the log round trip."""
+        `fov` [B,V,1] degrees, `resolution`) and leave rays_d / tri_vpos_view_tf None.  `tf32_view_tf`
+        is accepted and ignored (one precision policy).  The pipeline calls the engine
+        directly and skips the log round trip."""
+        if rays_o is not None and bool((rays_o != 0).any()):
+            # the reference rotates the queries with RoPE at ray_pos = rays_o (view_transformer.py:109,
+            # attention.py:668-671); this engine hard-wires the camera-space identity (origin 0)
+            raise ValueError("RenderFormer.forward: rays_o must be 0 (camera-space rays, as the pipeline passes them)")
         eng = self.engine()
         st = eng.encode_scene(tri_vpos_list, texture_patch_list, valid_mask, vns, texture_is_log=True)
         if rays_d is not None and tri_vpos_view_tf is not None:
@@ -153,17 +158,21 @@ class RenderFormerRenderingPipeline:
         self.model.to(device)
 
     @torch.no_grad()
-    def encode(self, triangles, texture, mask, vn) -> SceneState:
+    def encode(self, triangles, texture, mask, vn, shard=None, texture_own_rows: bool = False) -> SceneState:
         """View-independent stage only (exposed for multi-GPU view sharding).  With `cuda_graphs` the
-        returned SceneState is the graph's static output (overwritten by the next call of that shape)."""
+        returned SceneState is the graph's static output (overwritten by the next call of that shape).
+        `shard` (engine.RowShard, see renderformer_b200.dist.row_shard) splits the token rows of the
+        stage over the ranks; every rank passes the same scene and gets the complete state."""
         eng = self.model.engine()
         inputs = (triangles, texture, mask, vn)
+        kw = dict(shard=shard, texture_own_rows=texture_own_rows)
         if self.cuda_graphs and all(t.is_cuda for t in inputs):
-            st = self._graph_entry(("encode", id(eng)) + self._sig(inputs), inputs,
-                                   lambda a, b, c, d: eng.encode_scene(a, b, c, d))
+            tag = ("encode", id(eng)) if shard is None else ("encode", id(eng), shard.rank, shard.world, texture_own_rows)
+            st = self._graph_entry(tag + self._sig(inputs), inputs,
+                                   lambda a, b, c, d: eng.encode_scene(a, b, c, d, **kw))
             st.static = True
             return st
-        return eng.encode_scene(triangles, texture, mask, vn)
+        return eng.encode_scene(triangles, texture, mask, vn, **kw)
 
     @torch.no_grad()
     def render_views(self, state: SceneState, c2w, fov, resolution: int = 512, _eager: bool = False) -> torch.Tensor:
@@ -173,6 +182,8 @@ class RenderFormerRenderingPipeline:
             return self._graph_entry(("views", id(eng), id(state), resolution, self.view_chunk) + self._sig((c2w, fov)),
                                      (c2w, fov), lambda a, b: self.render_views(state, a, b, resolution, _eager=True))
         B, V = c2w.shape[:2]
+        if V == 0:  # a rank whose view slice is empty (fewer views than ranks)
+            return torch.empty((B, 0, resolution, resolution, 3), dtype=torch.float32, device=self.device)
         jobs = [(b, v0) for b in range(B) for v0 in range(0, V, self.view_chunk)]
         n_str = min(self.view_streams, len(jobs))
         if n_str <= 1:
@@ -246,7 +257,9 @@ class RenderFormerRenderingPipeline:
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
-            with torch.cuda.graph(graph):
+            # thread_local: torch.distributed's watchdog thread keeps polling events while a graph with NCCL
+            # collectives inside (row-sharded scene stage) is being captured
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_out = fn(*static_in)
             entry = self._graphs[key] = (graph, static_in, static_out, L.launch_count() - n0)
         graph, static_in, static_out, n_kernels = entry

@@ -21,19 +21,35 @@ _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
 PROFILE = None
 
 
+# Device every launch is bound to.  The C launchers run on the CUDA context's *current* device with
+# the stream they are handed, so both must belong to the tensors' device: `_need_cuda` records the
+# device of the operands, `_stream` returns that device's current stream and `_timed` makes it the
+# current device around the launch (a model on cuda:1 while cuda:0 is current must not launch on
+# GPU0 against GPU1 pointers -- ADVICE r01).
+_DEV = [None]
+
+
 def _timed(kind: str, flops: float, launch, tag: str = ""):
+    dev = _DEV[0]
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _timed_on_device(kind, flops, launch, tag)
+    return _timed_on_device(kind, flops, launch, tag)
+
+
+def _timed_on_device(kind: str, flops: float, launch, tag: str):
     if PROFILE is None:
         return launch()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(torch.cuda.current_stream())
     rc = launch()
-    e1.record()
+    e1.record(torch.cuda.current_stream())
     PROFILE.append((kind, flops, e0, e1, tag))
     return rc
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(_DEV[0]).cuda_stream
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -41,9 +57,17 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _need_cuda(*ts):
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise L.RfbError("renderformer_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise L.RfbError(f"operands live on different devices ({dev} vs {t.device})")
+    _DEV[0] = dev
 
 
 def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *, M=None, N=None, K=None,
@@ -149,7 +173,8 @@ def rowstat(x, out16, sumsq, *, rows, d):
     """sumsq: [rows, parts] partial-sum layout (total in part 0, the rest cleared)."""
     _need_cuda(x, out16, sumsq)
     L.check(_timed("rowstat", 0.0, lambda: L.load().rfb_rowstat(
-        x.data_ptr(), out16.data_ptr(), _DT[out16.dtype], sumsq.data_ptr(), sumsq.stride(0), sumsq.shape[1], rows, d,
+        x.data_ptr(), out16.data_ptr(), _DT[out16.dtype], out16.stride(0), sumsq.data_ptr(), sumsq.stride(0),
+        sumsq.shape[1], rows, d,
         _stream())), "rfb_rowstat")
     return out16, sumsq
 
@@ -223,16 +248,19 @@ def cast(x, out):
 
 
 def pixel_shuffle(x, out, *, B, h, w, s, C_):
+    _need_cuda(x, out)
     L.check(_timed("pixel_shuffle", 0.0, lambda: L.load().rfb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, h, w, s, C_, _stream())), "rfb_pixel_shuffle")
     return out
 
 
 def im2col_s2(x, out, *, B, H, W, C_):
+    _need_cuda(x, out)
     L.check(_timed("im2col_s2", 0.0, lambda: L.load().rfb_im2col_s2(x.data_ptr(), out.data_ptr(), B, H, W, C_, _stream())), "rfb_im2col_s2")
     return out
 
 
 def upsample_bilinear(x, out, *, B, Hi, Wi, Ho, Wo, C_):
+    _need_cuda(x, out)
     L.check(_timed("upsample_bilinear", 0.0, lambda: L.load().rfb_upsample_bilinear(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C_, _stream())), "rfb_upsample_bilinear")
     return out
 

@@ -6,8 +6,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from renderformer_b200.dist import broadcast_scene_state, gather_images, view_slice
-from renderformer_b200.engine import SceneState
+from renderformer_b200.dist import broadcast_scene_state, gather_images, row_shard, view_slice
+from renderformer_b200.engine import RowShard, SceneState
 
 
 def _free_port():
@@ -39,6 +39,16 @@ def _worker(rank, world, port, q):
             ok = ok and out.shape == (5, 2, 2, 3) and torch.equal(out[:, 0, 0, 0], torch.arange(5.0))
         else:
             ok = ok and out is None
+        # the per-layer collective of the row-sharded scene stage: in-place all-gather of the own chunk
+        sh = row_shard()
+        ok = ok and sh is not None and (sh.rank, sh.world) == (rank, world)
+        ntp = 40
+        S = sh.shard_rows(ntp)
+        full = torch.full((world * S, 6), -1.0)
+        r0, r1 = sh.my_rows(ntp)
+        full[r0:r1] = torch.arange(r0, r1, dtype=torch.float32)[:, None].expand(-1, 6)
+        sh.all_gather(full, full[rank * S:(rank + 1) * S])
+        ok = ok and torch.equal(full[:ntp, 0], torch.arange(float(ntp)))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -51,6 +61,19 @@ def test_view_slice_partitions():
             assert idx == list(range(n))
             sizes = [len(range(n)[view_slice(n, w, r)]) for r in range(w)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_row_shard_partitions():
+    """Rows are partitioned contiguously in multiples of 8; trailing ranks may own nothing."""
+    for ntp in (8, 24, 40, 1040, 4112, 5656, 8208):
+        for w in (1, 2, 4, 8):
+            shards = [RowShard(r, w, None) for r in range(w)]
+            S = shards[0].shard_rows(ntp)
+            assert S % 8 == 0 and w * S >= ntp
+            rows = [sh.my_rows(ntp) for sh in shards]
+            assert rows[0][0] == 0 and rows[-1][1] == ntp
+            assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+            assert all(0 <= r1 - r0 <= S for r0, r1 in rows)
 
 
 def test_broadcast_and_gather_world2():

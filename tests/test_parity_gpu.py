@@ -15,13 +15,34 @@ from renderformer_b200.synth import init_state_dict, make_scene
 pytestmark = pytest.mark.gpu
 
 
-def _pipeline(cfg, wseed):
+_PIPES = {}
+
+
+def _pipeline(cfg, wseed, name=None):
+    """One pipeline per (architecture, weight seed): the 483M-parameter model is initialised, uploaded and
+    re-laid out once for all the Large cases."""
     from renderformer_b200.model import RenderFormer, RenderFormerRenderingPipeline
+    key = (name, wseed)
+    if name is not None and key in _PIPES:
+        return _PIPES[key]
     model = RenderFormer(cfg)
     model.load_state_dict(init_state_dict(cfg, wseed))
     pipe = RenderFormerRenderingPipeline(model)
     pipe.to(torch.device("cuda:0"))
+    if name is not None:
+        _PIPES.clear()  # keep at most one cached model resident
+        _PIPES[key] = pipe
     return pipe
+
+
+def _case_scene(c, golden_dir):
+    """Host tensors of a golden case, exactly as oracle/make_golden.py:build_scene made them."""
+    if c.get("scene") == "cbox":
+        from renderformer_b200 import scene_io as sio
+        return sio.to_pipeline_inputs(sio.load_npz(os.path.join(golden_dir, "cbox_scene.npz")))
+    n = c["n_tris"]
+    scenes = [make_scene(n, c["views"], seed=c["scene_seed"] + b, pad_to=c["pad_to"]) for b in range(c.get("batch", 1))]
+    return {k: torch.cat([sc[k] for sc in scenes], dim=0) for k in scenes[0]}
 
 
 def _cases(golden_dir):
@@ -29,25 +50,42 @@ def _cases(golden_dir):
         return json.load(f)["cases"]
 
 
-@pytest.mark.parametrize("name", ["tiny_swin_a", "tiny_full_a", "tiny_swin_b", "large_small", "base_small",
-                                  "large_4096_512"])
+# every configuration a throughput figure is quoted on has its own reference-generated fixture:
+# large_4096_512 (north_star frame), _v4 (the bench's 4-view chunk), large_cbox_512 (BASELINE configs[1]),
+# large_1024_1024 (16384 ray tokens), large_8192_256 (8192 triangles), large_b2 (two scenes per call)
+@pytest.mark.parametrize("name", ["tiny_swin_a", "tiny_full_a", "tiny_swin_b", "base_small", "large_small",
+                                  "large_b2", "large_4096_512", "large_4096_512_v4", "large_cbox_512",
+                                  "large_1024_1024", "large_8192_256"])
 def test_golden_image(name, golden_dir):
     c = _cases(golden_dir)[name]
     cfg = RenderFormerConfig.named(c["config"])
-    pipe = _pipeline(cfg, c["weight_seed"])
-    sc = make_scene(c["n_tris"], c["views"], seed=c["scene_seed"], pad_to=c["pad_to"])
-    sc = {k: v.cuda() for k, v in sc.items()}
+    pipe = _pipeline(cfg, c["weight_seed"], c["config"])
+    pipe.cuda_graphs = False
+    sc = {k: v.cuda() for k, v in _case_scene(c, golden_dir).items()}
     tex_before = sc["texture"].clone()
     img = pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"],
                resolution=c["resolution"], torch_dtype=torch.bfloat16)
     assert torch.equal(tex_before, sc["texture"]), "caller's texture must not be modified"
     gold = np.load(os.path.join(golden_dir, f"{name}.npz"))
     ref = torch.from_numpy(gold["hdr"])
-    assert img.shape == ref.shape and img.dtype == torch.float32
+    hs = c.get("hdr_stride", 1)
+    assert img.shape[:2] == ref.shape[:2] and img.shape[2] == c["resolution"] and img.dtype == torch.float32
     assert torch.isfinite(img).all()
+    full_img = img
+    img = img[:, :, ::hs, ::hs]  # big frames are stored pixel-subsampled
+    assert img.shape == ref.shape
+
+    if name == "large_b2":  # the same call replayed from a CUDA graph (B = 2): bit-identical to eager launches
+        pipe.cuda_graphs = True
+        for _ in range(2):
+            g = pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"],
+                     resolution=c["resolution"], torch_dtype=torch.bfloat16)
+            assert torch.equal(g, full_img)
+        pipe.cuda_graphs = False
+        pipe._graphs.clear()
 
     st = pipe.encode(sc["triangles"], sc["texture"], sc["mask"], sc["vn"])
-    nt = c["n_tris"] + 16
+    nt = c["n_tris"] + 16  # valid rows only: padded rows are don't-care (layers/attention.py:173)
     stride = c.get("seq_row_stride", 1)
     gold_seq = torch.from_numpy(gold["seq"].astype(np.float32))[:, :(nt + stride - 1) // stride]
     seq_err = rel_l2(st.seq[:, :nt:stride].float(), gold_seq)
