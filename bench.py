@@ -339,7 +339,7 @@ def main():
     model.load_state_dict(init_state_dict(cfg, 7))
     pipe = RenderFormerRenderingPipeline(model)
     pipe.to(dev)
-    model.engine()
+    model.engine(torch.bfloat16)
     R, N = args.resolution, args.tris
     V = job_views(args, world)
     pipe.view_chunk = max(1, args.view_chunk)
@@ -365,7 +365,7 @@ def main():
             return pipe.render(inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w"], inp["fov"],
                                resolution=R, torch_dtype=torch.bfloat16)
         return render_sharded(pipe, inp["triangles"], inp["texture"], inp["mask"], inp["vn"], inp["c2w"], inp["fov"],
-                              resolution=R, dst=dst)
+                              resolution=R, dst=dst, torch_dtype=torch.bfloat16)
 
     def step_e2e():
         """Public API with HOST buffers, one blocking call per step: H2D of the step's inputs, render, D2H."""
@@ -435,7 +435,8 @@ def main():
         else:
             def stream_steps(n):
                 sink = 0.0
-                for _mine, img in render_stream_sharded(pipe, (host_scene for _ in range(n)), resolution=R):
+                for _mine, img in render_stream_sharded(pipe, (host_scene for _ in range(n)), resolution=R,
+                                                        torch_dtype=torch.bfloat16):
                     sink += float(img[0, 0, 0, 0, 0]) if img.numel() else 0.0
                 return sink
             api = ("renderformer_b200.dist.render_stream_sharded (every rank uploads the geometry and its own rows of the "

@@ -49,7 +49,8 @@ enum { RFB_A_LINEAR = 0, RFB_A_CONV3X3 = 1 };
 enum {
   RFB_EPI_STORE = 0,  /* v = acc (+bias) (+res1) (+res2); out = v; out_act = silu(v) */
   RFB_EPI_SWIGLU = 1, /* W rows interleaved [16 gate | 16 up] per 32: out[:, n/2] = silu(g)*u */
-  RFB_EPI_FINAL = 2   /* N==32: y = w2 * silu(acc+bias) + b2 (3 ch); out = 10^elu(y) - 1, fp32 */
+  RFB_EPI_FINAL = 2,  /* N==32: y = w2 * silu(acc+bias) + b2 (3 ch); out = 10^elu(y) - 1, fp32 */
+  RFB_EPI_FINAL_RAW = 3 /* as FINAL but out = y: DPTHead.forward's own return value (layers/dpt.py:271) */
 };
 
 typedef struct {
@@ -114,7 +115,7 @@ typedef struct {
 int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
- * rfb_attention: O = softmax(scale * Q K^T + mask) V, head_dim 128, bf16 in/out, fp32
+ * rfb_attention: O = softmax(scale * Q K^T + mask) V, head_dim 128, bf16 or fp16 in/out, fp32
  * softmax and accumulation (tcgen05 flash-style kernel, S and O live in TMEM).
  *
  * Replaces F.scaled_dot_product_attention / flash_attn_* at layers/attention.py:143-198
@@ -153,6 +154,7 @@ typedef struct {
   int sumsq_parts;
   int norm_dim;
   float norm_eps;
+  int dtype; /* operand type of Q, K, Vt and O: RFB_BF16 (also 0 = unset) or RFB_F16 */
 } rfb_attn_args;
 
 int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
@@ -167,18 +169,27 @@ int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
 int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* out, int out_dtype, long long ldo,
                 int rows, int d, float eps, const int* gather, rfb_stream_t stream);
 
-/* out16[r*ld16 + :] = cast(x[r,:]) (16-bit), sumsq[r*sumsq_ld] = sum(x[r,:]^2), sumsq[r*sumsq_ld + 1..parts) = 0:
+/* (input row = gather ? gather[r] : r: torch.roll + window_partition, layers/attention.py:334-339, folded into the read)
+ * out16[r*ld16 + :] = cast(x[r,:]) (16-bit), sumsq[r*sumsq_ld] = sum(x[r,:]^2), sumsq[r*sumsq_ld + 1..parts) = 0:
  * seeds the fused-norm GEMM chain (the input side of nn.RMSNorm, layers/attention.py:503-526,
  * without materialising norm(x)) in the partial-sum layout rfb_gemm's out_sumsq uses. */
 int rfb_rowstat(const float* x, void* out16, int out_dtype, long long ld16, float* sumsq, int sumsq_ld, int parts,
-                int rows, int d, rfb_stream_t stream);
+                int rows, int d, const int* gather, rfb_stream_t stream);
 
 /* QK-RMSNorm over the full model width + triangle RoPE (layers/attention.py:128-141,
- * encodings/rope.py:78-149,152-206): fp32 [rows, nseg*d] -> bf16.  Input row = r % in_period
+ * encodings/rope.py:78-149,152-206): fp32 [rows, nseg*d] -> 16 bit (out_dtype RFB_BF16 / RFB_F16).  Input row = r % in_period
  * when in_period > 0 (one hoisted pre-RoPE K re-rotated for every view).  pos [rows,9] or NULL. */
-int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out, long long ldo,
-                    int rows, int d, int nseg, float eps, const float* pos, const float* freqs, int nfreq,
-                    rfb_stream_t stream);
+int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out, int out_dtype,
+                    long long ldo, int rows, int d, int nseg, float eps, const float* pos, const float* freqs,
+                    int nfreq, rfb_stream_t stream);
+
+/* The same with READY-MADE rotation tables, as MultiHeadAttention.forward receives them (layers/attention.py:115:
+ * rope_cos / rope_sin [rows, ldtab >= 64] fp32 from freqs_to_cos_sin, encodings/rope.py:78-103): pair (i, i+64) of
+ * every head rotates by (cos_tab[r][i], sin_tab[r][i]).  NULL tables = QK-RMSNorm only; w == NULL = rotation
+ * only (apply_rotary_emb_one_cossin, encodings/rope.py:132-149). */
+int rfb_qknorm_rope_table(const float* x, long long ldx, const float* w, void* out, int out_dtype, long long ldo,
+                          int rows, int d, int nseg, float eps, const float* cos_tab, const float* sin_tab,
+                          long long ldtab, rfb_stream_t stream);
 
 /* out[b, n_prefix + i, :] = token + RMSNorm(a[b,i]) * wa (+ RMSNorm(b[b,i]) * wb); rows
  * [0,n_prefix) = prefix; rows past n_prefix + rows_in are zero.  models/renderformer.py:139-163,
@@ -205,6 +216,10 @@ int rfb_vn_encode(const float* vn, void* out, int n, int nfreq, int ld, rfb_stre
 /* camera-space ray bundles -> patch tokens f16 [V, (R/8)^2, 192] (utils/ray_generator.py:13-50,
  * models/view_transformer.py:104-107); fov in degrees. */
 int rfb_ray_tokens(const float* fov_deg, void* out, int n_views, int resolution, rfb_stream_t stream);
+
+/* RayGenerator.forward (utils/ray_generator.py:13-50) for callers that want the ray map itself: c2w [V,4,4],
+ * fov in RADIANS [V] -> rays_d fp32 [V, R, R, 3] (rotated by R(c2w), L2-normalised). */
+int rfb_ray_map(const float* c2w, const float* fov_rad, float* rays_d, int n_views, int resolution, rfb_stream_t stream);
 
 /* explicit ray map fp32 [V, R, R, 3] -> patch tokens f16 [V, (R/8)^2, 192] (models/view_transformer.py:104-107):
  * the model-level entry RenderFormer.forward(..., rays_d, tri_vpos_view_tf) hands rays in instead of cameras. */

@@ -72,6 +72,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t t2, float& p0, float& p1) {
 }
 constexpr uint32_t kAttn2Smem = kT2 * (2 + 2 * kStg) + 1024 + 256;
 
+template <bool F16>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
     attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
   } else if (warp == 1) {
     setmaxnreg_dec<kRegsWg0>();
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
+      const uint32_t idesc = umma_idesc_f16(F16 ? 0u : 1u, 128, 128);
       auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T
         const int s = j % kStg;
         const uint64_t ad = umma_desc_sw128(smem_u32(sQ + t * kT2));
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
             p0 = ex2_f(lo2f(t2)), p1 = ex2_f(hi2f(t2));
           }
           rs2[i & 3] = fadd2(rs2[i & 3], pack2f(p0, p1));
-          pk[i] = pack_bf16(p0, p1);
+          pk[i] = pack16<F16>(p0, p1);
         }
         tmem_st16(tS + c * 16, pk);
       }
@@ -318,10 +319,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
-          u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+          u.x = pack16<F16>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+          u.y = pack16<F16>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+          u.z = pack16<F16>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+          u.w = pack16<F16>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
           *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
         }
       }
@@ -350,16 +351,18 @@ int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   p.q_sumsq = a->q_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
   p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
-  static PerDeviceFlag attr_flags;
-  bool& attr_set = attr_flags.get();
+  const bool f16 = a->dtype == RFB_F16;
+  auto kern = f16 ? attn2_tc_kernel<true> : attn2_tc_kernel<false>;
+  static PerDeviceFlag attr_flags[2];
+  bool& attr_set = attr_flags[f16].get();
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem) !=
         cudaSuccess)
       return RFB_ERR_LAUNCH;
     // setmaxnreg moves registers inside the CTA's launch allocation only: the softmax warpgroups'
     // request must be covered by what warpgroup 0 gives back, or the kernel would wait forever
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, attn2_tc_kernel) != cudaSuccess) return RFB_ERR_LAUNCH;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return RFB_ERR_LAUNCH;
     if (128 * kRegsWg0 + 256 * kRegsSoftmax > kAttn2Threads * fa.numRegs) {
       fprintf(stderr, "rfb: attn2_tc_kernel compiled with %d registers/thread; setmaxnreg split %d/%d does not fit\n",
               fa.numRegs, kRegsWg0, kRegsSoftmax);
@@ -368,7 +371,7 @@ int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
     attr_set = true;
   }
   dim3 grid((a->Nq + 255) / 256, a->H, a->B);
-  attn2_tc_kernel<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, kAttn2Threads, kAttn2Smem, stream>>>(tmQ, tmK, tmV, p);
   g_launch_count++;
   return check_launch("attn2_tc_kernel");
 }

@@ -62,6 +62,7 @@ __device__ __forceinline__ void exp2_poly2_3(uint64_t t2, float& p0, float& p1) 
   p1 = __uint_as_float(__float_as_uint(hi2f(p)) + (__float_as_uint(hi2f(r)) << 23));
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kAttn3Threads, 1)
     attn3_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const Attn3Params p) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
+      const uint32_t idesc = umma_idesc_f16(F16 ? 0u : 1u, 128, 128);
       auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T, A operand = Q in TMEM (packed bf16 pairs)
         const int s = j % kStg3;
         mbar_wait(&k_full[s], (j / kStg3) & 1);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
             p0 = ex2_f(lo2f(t2)), p1 = ex2_f(hi2f(t2));
           }
           rs2[i & 3] = fadd2(rs2[i & 3], pack2f(p0, p1));
-          pk[i] = pack_bf16(p0, p1);
+          pk[i] = pack16<F16>(p0, p1);
         }
         tmem_st16(tS + c * 16, pk);
       }
@@ -305,10 +306,10 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
-          u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+          u.x = pack16<F16>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+          u.y = pack16<F16>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+          u.z = pack16<F16>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+          u.w = pack16<F16>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
           *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
         }
       }
@@ -340,15 +341,17 @@ int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_
   p.q_sumsq = a->q_sumsq, p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1;
   p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
-  static PerDeviceFlag attr_flags;
-  bool& attr_set = attr_flags.get();
+  const bool f16 = a->dtype == RFB_F16;
+  auto kern = f16 ? attn3_tc_kernel<true> : attn3_tc_kernel<false>;
+  static PerDeviceFlag attr_flags[2];
+  bool& attr_set = attr_flags[f16].get();
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3Smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3Smem) != cudaSuccess)
       return RFB_ERR_LAUNCH;
     attr_set = true;
   }
   dim3 grid((a->Nq + 127) / 128, a->H, a->B);
-  attn3_tc_kernel<<<grid, kAttn3Threads, kAttn3Smem, stream>>>(tmK, tmV, p);
+  kern<<<grid, kAttn3Threads, kAttn3Smem, stream>>>(tmK, tmV, p);
   g_launch_count++;
   return check_launch("attn3_tc_kernel");
 }

@@ -53,6 +53,7 @@ __device__ __forceinline__ float sw_rms_factor(const float* sumsq, long long row
   return rsqrtf(ss * inv_dim + eps);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kSwThreads, 1)
     attn_swin_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const SwinParams p) {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kSwThreads, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(1u, 128, 128);
+      const uint32_t idesc = umma_idesc_f16(F16 ? 0u : 1u, 128, 128);
       auto issue_qk = [&](int h) {  // S[h&1] = Q_h K_h^T  (the buffer's previous P was consumed by PV(h-2),
         const int s = h & 1;        //  issued earlier: tcgen05 operations of one thread retire in order)
         mbar_wait(&full[s], (h >> 1) & 1);
@@ -204,10 +205,10 @@ __global__ void __launch_bounds__(kSwThreads, 1)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-            u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-            u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-            u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+            u.x = pack16<F16>(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+            u.y = pack16<F16>(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+            u.z = pack16<F16>(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+            u.w = pack16<F16>(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
             *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = u;
           }
         }
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kSwThreads, 1)
               ffma2(pack2f(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2_2, nms_2);
           const float p0 = ex2_f(lo2f(t2)), p1 = ex2_f(hi2f(t2));
           rs2[i & 1] = fadd2(rs2[i & 1], pack2f(p0, p1));
-          pk[i] = pack_bf16(p0, p1);
+          pk[i] = pack16<F16>(p0, p1);
         }
         tmem_st16(tS + half * 32 + c * 16, pk);
       }
@@ -298,15 +299,17 @@ int launch_attention_swin(const CUtensorMap& tmQ, const CUtensorMap& tmK, const 
   p.q_sumsq = a->q_sumsq, p.k_sumsq = a->k_sumsq;
   p.sumsq_ld = a->sumsq_ld > 0 ? a->sumsq_ld : 1, p.sumsq_parts = a->sumsq_parts > 0 ? a->sumsq_parts : 1;
   p.inv_norm_dim = a->norm_dim > 0 ? 1.0f / (float)a->norm_dim : 0.f, p.norm_eps = a->norm_eps;
-  static PerDeviceFlag attr_flags;
-  bool& attr_set = attr_flags.get();
+  const bool f16 = a->dtype == RFB_F16;
+  auto kern = f16 ? attn_swin_kernel<true> : attn_swin_kernel<false>;
+  static PerDeviceFlag attr_flags[2];
+  bool& attr_set = attr_flags[f16].get();
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_swin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmem) != cudaSuccess)
       return RFB_ERR_LAUNCH;
     attr_set = true;
   }
   dim3 grid((a->Nq + 127) / 128, a->B);
-  attn_swin_kernel<<<grid, kSwThreads, kSwSmem, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, kSwThreads, kSwSmem, stream>>>(tmQ, tmK, tmV, p);
   g_launch_count++;
   return check_launch("attn_swin_kernel");
 }

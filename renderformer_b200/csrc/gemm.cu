@@ -175,7 +175,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long o
       }
       store8(p.out, p.out_dtype, orow * p.ldo + (n0 >> 1) + g * 8, h);
     }
-  } else {  // RFB_EPI_FINAL (N == 32, n0 == 0)
+  } else {  // RFB_EPI_FINAL / RFB_EPI_FINAL_RAW (N == 32, n0 == 0)
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) h[j] = silu_f(__uint_as_float(v[j]) + __ldg(p.bias + j));
@@ -185,8 +185,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long long o
       float y = __ldg(p.b2 + c);
 #pragma unroll
       for (int j = 0; j < 32; ++j) y = fmaf(__ldg(p.w2 + c * 32 + j), h[j], y);
-      y = y > 0.f ? y : 1e-3f * expm1f(y);  // ELU(alpha=1e-3)  view_transformer.py:86,122
-      o[c] = exp10f(y) - 1.0f;              // rendering_pipeline.py:122-123
+      if (p.epi == RFB_EPI_FINAL_RAW) {
+        o[c] = y;                             // DPTHead.forward's own output  layers/dpt.py:271
+      } else {
+        y = y > 0.f ? y : 1e-3f * expm1f(y);  // ELU(alpha=1e-3)  view_transformer.py:86,122
+        o[c] = exp10f(y) - 1.0f;              // rendering_pipeline.py:122-123
+      }
     }
   }
 }
@@ -234,6 +238,11 @@ __device__ __forceinline__ void store4(void* base, int dtype, long long idx, con
 constexpr int EK_GENERIC = 0;
 constexpr int EK_RESID = 1;   // out f32 = acc*r + res1 f32, + bf16 copy + partial sums of squares
 constexpr int EK_PROJ16 = 2;  // out16 bf16 = acc*r*col_mul only, + partial sums of squares
+constexpr int EK_RESID_H = 3;   // the same two with an fp16 (half) 16-bit side output
+constexpr int EK_PROJ16_H = 4;
+__host__ __device__ constexpr bool ek_resid(int ek) { return ek == EK_RESID || ek == EK_RESID_H; }
+__host__ __device__ constexpr bool ek_fast(int ek) { return ek >= EK_RESID && ek <= EK_PROJ16_H; }
+__host__ __device__ constexpr bool ek_half(int ek) { return ek == EK_RESID_H || ek == EK_PROJ16_H; }
 // EK >= EK_CONV: the generic epilogue with its flags fixed at compile time for the DPT convolutions
 // (fp16 in / out, 128-wide tile): EK = EK_CONV + mask, mask bits below
 constexpr int EK_CONV = 16;
@@ -480,7 +489,8 @@ template <int EK>
 __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, float* stage, int lane, uint32_t taddr,
                                                         int n_begin, int orow_mine, int arow_mine, float rs_mine,
                                                         uint64_t* tfull_bar, uint32_t parity) {
-  constexpr bool RES = EK == EK_RESID;
+  constexpr bool RES = ek_resid(EK);
+  constexpr bool O16H = ek_half(EK);
   const int c4 = lane & 7;
   const int g4 = lane >> 3;
   int orow[8], arow[8];
@@ -540,7 +550,7 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
         }
         sqp[it] += x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
         uint2 u;
-        u.x = pack_bf16(x[0] * cm[0], x[1] * cm[1]), u.y = pack_bf16(x[2] * cm[2], x[3] * cm[3]);
+        u.x = pack16<O16H>(x[0] * cm[0], x[1] * cm[1]), u.y = pack16<O16H>(x[2] * cm[2], x[3] * cm[3]);
         *reinterpret_cast<uint2*>(out16 + (long long)arow[it] * p.ld16 + n) = u;
       }
     }
@@ -562,7 +572,7 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
 
 
 template <int BN, int EK>
-__global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads, 1)
+__global__ void __launch_bounds__(ek_resid(EK) ? kGemmThreadsWG : kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -583,7 +593,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int EPI0 = (EK == EK_RESID) ? 4 : 2;  // first epilogue warp
+  constexpr int EPI0 = ek_resid(EK) ? 4 : 2;  // first epilogue warp
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();
+    if constexpr (ek_resid(EK)) setmaxnreg_dec<kRegsGemmWg0>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -647,7 +657,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();
+    if constexpr (ek_resid(EK)) setmaxnreg_dec<kRegsGemmWg0>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -673,10 +683,10 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
       }
     }
   } else if (warp < EPI0) {
-    if constexpr (EK == EK_RESID) setmaxnreg_dec<kRegsGemmWg0>();  // idle warps of warpgroup 0
+    if constexpr (ek_resid(EK)) setmaxnreg_dec<kRegsGemmWg0>();  // idle warps of warpgroup 0
   } else {
     // ------------------------------ epilogue ------------------------------
-    if constexpr (EK == EK_RESID) setmaxnreg_inc<kRegsGemmEpi>();
+    if constexpr (ek_resid(EK)) setmaxnreg_inc<kRegsGemmEpi>();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     int it = 0;
@@ -732,7 +742,7 @@ __global__ void __launch_bounds__(EK == EK_RESID ? kGemmThreadsWG : kGemmThreads
       if (p.vt_out && n0 >= p.vt_split) {  // tile of the transposed (V) part: warp-uniform per tile
         epilogue_vt_chunks(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, n0, c_begin, c_end,
                            mt * kBM + r, valid, rs, &tfull[as], aph);
-      } else if constexpr (EK == EK_RESID || EK == EK_PROJ16) {
+      } else if constexpr (ek_fast(EK)) {
         static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
         epilogue_half_tile_fast<EK>(p, my_stage, lane,
                                     tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
@@ -779,7 +789,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (cudaFuncSetAttribute(gemm_tc_kernel<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmemBytes) != cudaSuccess)
       return RFB_ERR_LAUNCH;
-    if (EK == EK_RESID) {  // setmaxnreg only moves registers inside the CTA's launch allocation
+    if (ek_resid(EK)) {  // setmaxnreg only moves registers inside the CTA's launch allocation
       cudaFuncAttributes fa;
       if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BN, EK>) != cudaSuccess) return RFB_ERR_LAUNCH;
       if (128 * kRegsGemmWg0 + 256 * kRegsGemmEpi > kGemmThreadsWG * fa.numRegs) {
@@ -790,7 +800,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     attr_set = true;
   }
-  constexpr int threads = (EK == EK_RESID) ? kGemmThreadsWG : kGemmThreads;
+  constexpr int threads = ek_resid(EK) ? kGemmThreadsWG : kGemmThreads;
   gemm_tc_kernel<BN, EK><<<grid, threads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   g_launch_count++;
   return check_launch("gemm_tc_kernel");
@@ -1035,7 +1045,8 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   if (a->in_sumsq && (a->norm_dim <= 0 || a->in_rscale || p.in_sumsq_parts > p.in_sumsq_ld)) return RFB_ERR_ARG;
   if (a->in_rscale && a->scale_dim != 0 && a->scale_dim != 1) return RFB_ERR_ARG;
   if (a->out_rscale && !a->in_sumsq) return RFB_ERR_ARG;
-  if (fused_any && a->epi == RFB_EPI_FINAL) return RFB_ERR_ARG;
+  const bool epi_final = a->epi == RFB_EPI_FINAL || a->epi == RFB_EPI_FINAL_RAW;
+  if (fused_any && epi_final) return RFB_ERR_ARG;
   if (a->epi == RFB_EPI_SWIGLU && (a->out_rscale || a->out_sumsq || a->out16 || a->col_mul ||
                                    (a->in_rscale && a->scale_dim != 0)))
     return RFB_ERR_ARG;
@@ -1075,7 +1086,7 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   } else if (a->epi == RFB_EPI_SWIGLU) {
     if (a->N % 32 || !a->out || a->out_dtype == RFB_F32 || a->ldo % 8) return RFB_ERR_ARG;
     p.n_store = a->N;
-  } else if (a->epi == RFB_EPI_FINAL) {
+  } else if (epi_final) {
     if (a->N != 32 || !a->out || !a->bias || !a->w2 || !a->b2) return RFB_ERR_ARG;
     bn = 32;
     p.n_store = 32;
@@ -1183,11 +1194,15 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
   int grid = (int)(total < cap ? total : cap);
 
-  if (bn == 256 && a->N % 256 == 0 && a->epi == RFB_EPI_STORE && !p.direct_store && a->out16 && a->out16_dtype == RFB_BF16 &&
+  if (bn == 256 && a->N % 256 == 0 && a->epi == RFB_EPI_STORE && !p.direct_store && a->out16 &&
       a->out_sumsq && !a->bias && !a->res2 && !a->out_act && !(a->in_rscale && a->scale_dim == 1)) {
+    const bool half = a->out16_dtype == RFB_F16;
     if (a->out && a->out_dtype == RFB_F32 && a->res1 && a->res_dtype == RFB_F32 && !a->col_mul)
-      return launch_gemm<256, EK_RESID>(tmA, tmB, p, grid, stream);
-    if (!a->out && !a->res1 && a->col_mul) return launch_gemm<256, EK_PROJ16>(tmA, tmB, p, grid, stream);
+      return half ? launch_gemm<256, EK_RESID_H>(tmA, tmB, p, grid, stream)
+                  : launch_gemm<256, EK_RESID>(tmA, tmB, p, grid, stream);
+    if (!a->out && !a->res1 && a->col_mul)
+      return half ? launch_gemm<256, EK_PROJ16_H>(tmA, tmB, p, grid, stream)
+                  : launch_gemm<256, EK_PROJ16>(tmA, tmB, p, grid, stream);
   }
   if (bn == 128 && a->a_mode == RFB_A_CONV3X3 && a->epi == RFB_EPI_STORE && !p.direct_store && !fused_any && !a->vt_out &&
       a->dtype == RFB_F16 && a->out_dtype == RFB_F16 && (!a->res1 || a->res_dtype == RFB_F16) && a->N % 128 == 0) {

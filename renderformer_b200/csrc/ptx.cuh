@@ -278,4 +278,11 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   return r;
 }
 
+// 16-bit pair in the operand format of the kernel instance (fp16 or bf16)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  if constexpr (F16) return pack_f16(lo, hi);
+  else return pack_bf16(lo, hi);
+}
+
 }  // namespace rfb

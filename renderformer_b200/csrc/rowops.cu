@@ -72,11 +72,12 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, long long ldx, const
 // (Seeds the (16-bit copy, sum of squares) pair that the residual GEMM epilogues then maintain.)
 // ---------------------------------------------------------------------------------------------
 __global__ void rowstat_kernel(const float* __restrict__ x, void* __restrict__ out16, int out_dtype, long long ld16,
-                               float* __restrict__ sumsq, int sumsq_ld, int parts, int rows, int d) {
+                               float* __restrict__ sumsq, int sumsq_ld, int parts, int rows, int d,
+                               const int* __restrict__ gather) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)(gather ? gather[row] : row) * d);
   const int nvec = d >> 7;
   float ss = 0.f;
 #pragma unroll
@@ -113,7 +114,9 @@ __global__ void __launch_bounds__(256, 3)
     qknorm_rope_rows_kernel(const float* __restrict__ x, long long ldx, int in_period,
                                    const float* __restrict__ w, void* __restrict__ out, long long ldo,
                                    int rows, int d, int nseg, float eps, const float* __restrict__ pos,
-                                   const float* __restrict__ freqs, int nfreq) {
+                                   const float* __restrict__ freqs, int nfreq, int out_dtype,
+                                   const float* __restrict__ ctab = nullptr, const float* __restrict__ stab = nullptr,
+                                   long long ldtab = 0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -125,7 +128,9 @@ __global__ void __launch_bounds__(256, 3)
   for (int e = 0; e < 4; ++e) {
     cs[e] = 1.f, sn[e] = 0.f;
     const int i = o + e;
-    if (pos && i < 9 * nfreq) {
+    if (ctab) {  // ready-made cos / sin tables (pair i rotates by entry i; entries 64.. duplicate 0..63)
+      cs[e] = ctab[(long long)row * ldtab + i], sn[e] = stab[(long long)row * ldtab + i];
+    } else if (pos && i < 9 * nfreq) {
       const float ang = pos[(long long)row * 9 + i / nfreq] * __ldg(freqs + i % nfreq);
       fast_sincos(ang, sn[e], cs[e]);
     }
@@ -149,14 +154,15 @@ __global__ void __launch_bounds__(256, 3)
       }
     }
     ss = warp_sum(ss);
-    const float r = rsqrtf(ss / d + eps);
+    const float r = w ? rsqrtf(ss / d + eps) : 1.0f;  // w == NULL: rotation only (apply_rotary_emb_one_cossin)
 #pragma unroll
     for (int it = 0; it < kMaxVec / 2; ++it) {
       const int u = it * 32 + lane;
       if (u < units) {
         const int base = (u >> 4) * 128 + o;
-        const float4 wl = __ldg(reinterpret_cast<const float4*>(ws + base));
-        const float4 wh = __ldg(reinterpret_cast<const float4*>(ws + base + 64));
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 wl = w ? __ldg(reinterpret_cast<const float4*>(ws + base)) : one4;
+        const float4 wh = w ? __ldg(reinterpret_cast<const float4*>(ws + base + 64)) : one4;
         const float a[4] = {lo[it].x * r * wl.x, lo[it].y * r * wl.y, lo[it].z * r * wl.z, lo[it].w * r * wl.w};
         const float b[4] = {hi[it].x * r * wh.x, hi[it].y * r * wh.y, hi[it].z * r * wh.z, hi[it].w * r * wh.w};
         float ra[4], rb[4];
@@ -166,8 +172,8 @@ __global__ void __launch_bounds__(256, 3)
           rb[e] = b[e] * cs[e] + a[e] * sn[e];
         }
         const long long idx = (long long)row * ldo + (long long)s * d + base;
-        store4_16(out, RFB_BF16, idx, ra[0], ra[1], ra[2], ra[3]);
-        store4_16(out, RFB_BF16, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+        store4_16(out, out_dtype, idx, ra[0], ra[1], ra[2], ra[3]);
+        store4_16(out, out_dtype, idx + 64, rb[0], rb[1], rb[2], rb[3]);
       }
     }
   }
@@ -179,7 +185,7 @@ constexpr int kRopeViews = 4;  // views rotated per pass over one source row (= 
 __global__ void __launch_bounds__(kRopeViews * 32, 6)
     qknorm_rope_kernel(const float* __restrict__ x, long long ldx, int in_period, const float* __restrict__ w,
                        void* __restrict__ out, long long ldo, int rows, int d, int nseg, float eps,
-                       const float* __restrict__ pos, const float* __restrict__ freqs, int nfreq) {
+                       const float* __restrict__ pos, const float* __restrict__ freqs, int nfreq, int out_dtype) {
   // One block (4 warps) per SOURCE row.  With in_period > 0 the same source row feeds
   // rows / in_period output rows (one per view, each with its own positions): warp v computes the
   // rotation table of view v once into shared memory, then the warps split the row's segments and
@@ -243,8 +249,8 @@ __global__ void __launch_bounds__(kRopeViews * 32, 6)
               rb[e] = b[e] * cs[e] + a[e] * sn[e];
             }
             const long long idx = ((long long)(v0 + vv) * src_rows + src) * ldo + (long long)s * d + base;
-            store4_16(out, RFB_BF16, idx, ra[0], ra[1], ra[2], ra[3]);
-            store4_16(out, RFB_BF16, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+            store4_16(out, out_dtype, idx, ra[0], ra[1], ra[2], ra[3]);
+            store4_16(out, out_dtype, idx + 64, rb[0], rb[1], rb[2], rb[3]);
           }
         }
       }
@@ -403,6 +409,26 @@ __global__ void ray_map_tokens_kernel(const float* __restrict__ rays, uint16_t* 
   out[t] = *reinterpret_cast<uint16_t*>(&h);
 }
 
+// Pinhole ray map of V cameras: rays_d [V, R, R, 3] fp32 = normalize(R_v * ((x - cx) / f, -(y - cy) / f, -1)),
+// pixel centres, f = R / 2 / tan(fov / 2), fov in RADIANS as RayGenerator.forward takes it
+// (utils/ray_generator.py:13-50).  One thread per pixel, 12-byte stores.
+__global__ void ray_map_kernel(const float* __restrict__ c2w, const float* __restrict__ fov_rad, float* __restrict__ out,
+                               int V, int R) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)V * R * R) return;
+  const int v = t / ((long long)R * R);
+  const int rem = t % ((long long)R * R);
+  const int py = rem / R, px = rem % R;
+  const float fl = (R * 0.5f) / tanf(0.5f * fov_rad[v]);
+  const float d[3] = {((px + 0.5f) - R * 0.5f) / fl, -((py + 0.5f) - R * 0.5f) / fl, -1.0f};
+  const float* m = c2w + (long long)v * 16;
+  float r[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = m[i * 4] * d[0] + m[i * 4 + 1] * d[1] + m[i * 4 + 2] * d[2];
+  const float inv = 1.0f / fmaxf(sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]), 1e-12f);
+  out[t * 3] = r[0] * inv, out[t * 3 + 1] = r[1] * inv, out[t * 3 + 2] = r[2] * inv;
+}
+
 // RoPE positions: pos[v, 0:n_reg] = masked vertex centroid (x3), pos[v, n_reg + i] = T_v^-1 tri_i.
 //   models/renderformer.py:103-124, utils/transform.py:7-27.  One block per view; c2w == NULL
 //   keeps world coordinates (the view-independent stage).
@@ -502,31 +528,44 @@ extern "C" int rfb_rmsnorm(const float* x, long long ldx, const float* w, void* 
 }
 
 extern "C" int rfb_rowstat(const float* x, void* out16, int out_dtype, long long ld16, float* sumsq, int sumsq_ld,
-                           int parts, int rows, int d, rfb_stream_t stream) {
+                           int parts, int rows, int d, const int* gather, rfb_stream_t stream) {
   if (!x || !out16 || !sumsq || rows <= 0 || d % 128 || d > kMaxVec * 128 || ld16 < d || ld16 % 4) return RFB_ERR_ARG;
   if (parts < 1 || parts > 32 || sumsq_ld < parts) return RFB_ERR_ARG;
   const int wpb = 8;
-  rowstat_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(x, out16, out_dtype, ld16, sumsq, sumsq_ld, parts, rows, d);
+  rowstat_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(x, out16, out_dtype, ld16, sumsq, sumsq_ld, parts, rows, d, gather);
   RFB_LAUNCHED("rowstat_kernel");
 }
 
-extern "C" int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out,
+extern "C" int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out, int out_dtype,
                                long long ldo, int rows, int d, int nseg, float eps, const float* pos,
                                const float* freqs, int nfreq, rfb_stream_t stream) {
   if (!x || !w || !out || rows <= 0 || d % 128 || d > kMaxVec * 128 || ldx % 4 || ldo % 4 || nseg < 1)
     return RFB_ERR_ARG;
+  if (out_dtype != RFB_BF16 && out_dtype != RFB_F16) return RFB_ERR_ARG;
   if (pos && (!freqs || nfreq < 1 || 9 * nfreq > 64)) return RFB_ERR_ARG;
   const int wpb = 8;
   if (in_period > 0 && rows % in_period) return RFB_ERR_ARG;
   const int src_rows = in_period > 0 ? in_period : rows;
   if (in_period == 0) {
     qknorm_rope_rows_kernel<<<dim3((rows + wpb - 1) / wpb, nseg), wpb * 32, 0, (cudaStream_t)stream>>>(
-        x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq);
+        x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq, out_dtype);
     RFB_LAUNCHED("qknorm_rope_rows_kernel");
   }
   qknorm_rope_kernel<<<src_rows, kRopeViews * 32, 0, (cudaStream_t)stream>>>(
-      x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq);
+      x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq, out_dtype);
   RFB_LAUNCHED("qknorm_rope_kernel");
+}
+
+extern "C" int rfb_qknorm_rope_table(const float* x, long long ldx, const float* w, void* out, int out_dtype,
+                                     long long ldo, int rows, int d, int nseg, float eps, const float* cos_tab,
+                                     const float* sin_tab, long long ldtab, rfb_stream_t stream) {
+  if (out_dtype != RFB_BF16 && out_dtype != RFB_F16) return RFB_ERR_ARG;
+  if (!x || !out || rows <= 0 || d % 128 || d > kMaxVec * 128 || ldx % 4 || ldo % 4 || nseg < 1) return RFB_ERR_ARG;
+  if ((cos_tab == nullptr) != (sin_tab == nullptr) || (cos_tab && ldtab < 64)) return RFB_ERR_ARG;
+  const int wpb = 8;
+  qknorm_rope_rows_kernel<<<dim3((rows + wpb - 1) / wpb, nseg), wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, ldx, 0, w, out, ldo, rows, d, nseg, eps, nullptr, nullptr, 0, out_dtype, cos_tab, sin_tab, ldtab);
+  RFB_LAUNCHED("qknorm_rope_rows_kernel");
 }
 
 extern "C" int rfb_token_assemble(const float* a, const float* wa, const float* b, const float* wb,
@@ -577,6 +616,15 @@ extern "C" int rfb_ray_tokens(const float* fov_deg, void* out, int n_views, int 
   ray_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fov_deg, (uint16_t*)out,
                                                                                        n_views, resolution);
   RFB_LAUNCHED("ray_tokens_kernel");
+}
+
+extern "C" int rfb_ray_map(const float* c2w, const float* fov_rad, float* rays_d, int n_views, int resolution,
+                           rfb_stream_t stream) {
+  if (!c2w || !fov_rad || !rays_d || n_views <= 0 || resolution <= 0) return RFB_ERR_ARG;
+  const long long total = (long long)n_views * resolution * resolution;
+  ray_map_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2w, fov_rad, rays_d, n_views,
+                                                                                    resolution);
+  RFB_LAUNCHED("ray_map_kernel");
 }
 
 extern "C" int rfb_ray_map_tokens(const float* rays_d, void* out, int n_views, int resolution, rfb_stream_t stream) {

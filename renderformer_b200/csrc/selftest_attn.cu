@@ -1,9 +1,15 @@
 // Standalone GPU self-test + micro-benchmark of rfb_attention (no torch).
+#include <stdlib.h>
 #include <string.h>
 
 #include "selftest_common.h"
 
-__device__ __forceinline__ float bf2f(uint16_t u) { return __uint_as_float((uint32_t)u << 16); }
+// operand format under test: bf16, or fp16 with RFB_TEST_F16=1 in the environment
+static int g_dt = RFB_BF16;
+__device__ int d_f16 = 0;
+__device__ __forceinline__ float bf2f(uint16_t u) {
+  return d_f16 ? __half2float(*reinterpret_cast<const __half*>(&u)) : __uint_as_float((uint32_t)u << 16);
+}
 
 // one thread per (b, h, q): fp32 online softmax over all permitted keys
 __global__ void ref_attn(const uint16_t* Q, long long ldq, long long qbs, const uint16_t* K,
@@ -52,9 +58,9 @@ static void run(const ACase& c, bool timing_only = false) {
   const size_t nq = (size_t)c.B * c.Nq * D, nk = (size_t)Bkv * c.Nk * D, nv = (size_t)Bkv * D * ldvt;
   DevBuf<uint16_t> dQ(nq), dK(nk), dV(nv), dO(nq);
   if (!timing_only) {
-    dQ.up(rand16(nq, 1, 2.0f, RFB_BF16));
-    dK.up(rand16(nk, 2, 2.0f, RFB_BF16));
-    dV.up(rand16(nv, 3, 1.0f, RFB_BF16));
+    dQ.up(rand16(nq, 1, 2.0f, g_dt));
+    dK.up(rand16(nk, 2, 2.0f, g_dt));
+    dV.up(rand16(nv, 3, 1.0f, g_dt));
   } else {
     CK(cudaMemset(dQ.p, 0x3c, nq * 2));
     CK(cudaMemset(dK.p, 0x3c, nk * 2));
@@ -108,6 +114,7 @@ static void run(const ACase& c, bool timing_only = false) {
   a.key_mask_bits = c.masked ? dM.p : nullptr, a.mask_batch_stride_words = words;
   a.mode = c.mode, a.group_id = dG.p, a.group_period = c.period;
   a.scale = 0.08838834764831845f;
+  a.dtype = g_dt;
 
   if (timing_only) {
     for (int i = 0; i < 3; ++i) rfb_attention(&a, 0);
@@ -142,12 +149,20 @@ static void run(const ACase& c, bool timing_only = false) {
   std::vector<float> ref = dref.down();
   std::vector<uint16_t> ho = dO.down();
   std::vector<float> got(nq);
-  for (size_t i = 0; i < nq; ++i) got[i] = h162f(ho[i], RFB_BF16);
+  for (size_t i = 0; i < nq; ++i) got[i] = h162f(ho[i], g_dt);
   report(c.name, got, ref, 1.5e-2, 2e-2, D);
 }
 
 int main(int argc, char** argv) {
   const bool only_bench = argc > 1 && !strcmp(argv[1], "bench");
+  if (const char* e = getenv("RFB_TEST_F16")) {
+    if (e[0] == '1') {
+      g_dt = RFB_F16;
+      const int one = 1;
+      CK(cudaMemcpyToSymbol(d_f16, &one, sizeof(int)));
+      printf("selftest_attn: fp16 operands\n");
+    }
+  }
   if (!only_bench) {
     std::vector<ACase> cases = {
         {"1 tile  B1 H1 Nq128 Nk128", 1, 1, 128, 128, 0, 0, 0, 0},

@@ -190,7 +190,8 @@ static void run_case(const Case& c) {
 }
 
 // fused-RMSNorm plumbing: in_sumsq partial sums / in_rscale (row or column), out_rscale,
-// out_sumsq partial sums, out16 (+col_mul, aux map)
+// out_sumsq partial sums, out16 (+col_mul, aux map); the 16-bit side output is bf16, or fp16 with RFB_TEST_F16=1
+static int g_o16 = RFB_BF16;
 // kind: 0 = everything at once (generic epilogue), 1 = residual-stream shape (no col_mul -> EK_RESID when
 // N % 256 == 0), 2 = 16-bit projection shape (no fp32 out, no residual -> EK_PROJ16)
 static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool swiglu, bool use_map, bool with_res,
@@ -250,7 +251,7 @@ static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool
     a.epi = RFB_EPI_STORE, a.out = kind == 2 ? nullptr : dout.p, a.out_dtype = RFB_F32, a.ldo = N;
     if (with_res) a.res1 = dres.p, a.res_dtype = RFB_F32, a.ldres = N;
     if (want_sq) a.out_sumsq = dosq.p, a.out_sumsq_ld = nparts;
-    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = N, a.col_mul = kind == 1 ? nullptr : dcm.p;
+    a.out16 = do16.p, a.out16_dtype = g_o16, a.ld16 = N, a.col_mul = kind == 1 ? nullptr : dcm.p;
     if (kind == 1)
       for (auto& c : hcm) c = 1.0f;
     a.aux_row_map = use_map ? dmap.p : nullptr;
@@ -289,7 +290,7 @@ static void run_fused(const char* name, int M, int N, int K, int scale_dim, bool
   }
   std::string nm(name);
   if (kind != 2) report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, N);
-  report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * N, RFB_BF16), exp16, 2e-2, 1.2e-2, N);
+  report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * N, g_o16), exp16, 2e-2, 1.2e-2, N);
   if (want_sq) report((nm + " [sumsq]").c_str(), dosq.down(), expsq, 1e-2, 2e-3, nparts);
   if (scale_dim == 0) report((nm + " [rscale]").c_str(), drs.down(), hscale, 1e-5, 1e-4, 1);
 }
@@ -327,7 +328,7 @@ static void run_vt(const char* name, int M, int N, int K, int split, int rows_pe
   a.in_sumsq = dparts.p, a.in_sumsq_ld = parts, a.in_sumsq_parts = parts, a.norm_dim = norm_dim, a.norm_eps = eps;
   a.out_dtype = RFB_F32, a.ldo = split;
   if (proj16) {
-    a.out16 = do16.p, a.out16_dtype = RFB_BF16, a.ld16 = split, a.col_mul = dcm.p;
+    a.out16 = do16.p, a.out16_dtype = g_o16, a.ld16 = split, a.col_mul = dcm.p;
     a.out_sumsq = dosq.p, a.out_sumsq_ld = split / 128;
   } else {
     a.out = dout.p;
@@ -352,7 +353,7 @@ static void run_vt(const char* name, int M, int N, int K, int split, int rows_pe
     for (int n = split; n < N; ++n) expvt[((size_t)b * nv + (n - split)) * vt_ld + mr] = acc[(size_t)m * N + n] * hrs[m];
   }
   std::string nm(name);
-  if (proj16) report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * split, RFB_BF16), exp16, 2e-2, 1.2e-2, split);
+  if (proj16) report((nm + " [out16]").c_str(), to_float(do16.p, (size_t)M * split, g_o16), exp16, 2e-2, 1.2e-2, split);
   else report((nm + " [out]").c_str(), dout.down(), exp, 2e-3, 2e-3, split);
   report((nm + " [v^T]").c_str(), to_float(dvt.p, expvt.size(), RFB_BF16), expvt, 2e-2, 1.2e-2, (int)vt_ld);
 }
@@ -440,6 +441,9 @@ static void bench(const char* name, int M, int N, int K, int epi, int out_dtype,
 }
 
 int main(int argc, char** argv) {
+  if (const char* e = getenv("RFB_TEST_F16")) {
+    if (e[0] == '1') g_o16 = RFB_F16, printf("selftest_gemm: fp16 side outputs (EK_RESID_H / EK_PROJ16_H)\n");
+  }
   if (argc >= 8 && !strcmp(argv[1], "one")) {  // one M N K epi out_dtype bn
     // optional: conv_hw Cin batch
     bench("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]),

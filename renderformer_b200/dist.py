@@ -84,7 +84,7 @@ def gather_images(img: torch.Tensor, dst: int = 0, sizes: Optional[List[int]] = 
 
 @torch.no_grad()
 def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int = 512, dst: Optional[int] = 0,
-                   texture_own_rows: bool = False):
+                   texture_own_rows: bool = False, torch_dtype: torch.dtype = torch.float16):
     """`RenderFormerRenderingPipeline.render` on all ranks of the process group: every rank passes the
     SAME scene and the full camera list c2w [B,V,4,4] / fov [B,V,1]; the scene stage is row-sharded, each
     rank renders `view_slice(V)`, and the images are gathered on `dst` (returns [B,V,H,W,3] there and
@@ -97,9 +97,10 @@ def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int
     c2w_l, fov_l = c2w[:, mine].contiguous(), fov[:, mine].contiguous()
     sh = row_shard()
     if world == 1:
-        img = pipe.render(triangles, texture, mask, vn, c2w_l, fov_l, resolution=resolution)
+        img = pipe.render(triangles, texture, mask, vn, c2w_l, fov_l, resolution=resolution, torch_dtype=torch_dtype)
     else:
-        eng = pipe.model.engine()
+        from .model import operand_dtype
+        eng = pipe.model.engine(operand_dtype(torch_dtype))
         inputs = (triangles, texture, mask, vn, c2w_l, fov_l)
 
         def run(tri, tex, msk, vnn, cw, fv):
@@ -121,7 +122,8 @@ def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int
 
 
 @torch.no_grad()
-def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str] = None):
+def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str] = None,
+                          torch_dtype: torch.dtype = torch.float16):
     """Multi-GPU counterpart of `RenderFormerRenderingPipeline.render_stream`: every rank iterates the SAME
     sequence of host scene dicts (keys of `render`).  Each rank uploads the geometry and only ITS OWN
     rows of the texture (1/world of the 218 MB), the scene stage runs row-sharded, each rank renders its
@@ -134,7 +136,8 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
     world, rank = _world()
     main = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(dev)
-    eng = pipe.model.engine()
+    from .model import operand_dtype
+    eng = pipe.model.engine(operand_dtype(torch_dtype))
     sh = row_shard()
 
     def upload(sc):
@@ -162,7 +165,8 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
         pending = upload(nxt) if nxt is not None else None
         main.wait_event(ev)
         if sh is None:
-            img = pipe.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"], resolution=resolution)
+            img = pipe.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"], resolution=resolution,
+                              torch_dtype=torch_dtype)
         else:
             # full camera list is not needed here: the slice was taken on the host
             inputs = (d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"])

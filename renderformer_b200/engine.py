@@ -103,10 +103,24 @@ def swin_window_maps(Hp: int, Wp: int, shift: int, ws: int = 8):
     return perm.to(torch.int32), region.to(torch.uint8)
 
 
+ALL_PARTS = ("tokens", "ray", "encoder", "decoder", "dpt")
+
+
 class Engine:
-    def __init__(self, cfg: RenderFormerConfig, state_dict: Dict[str, torch.Tensor], device):
+    def __init__(self, cfg: RenderFormerConfig, state_dict: Dict[str, torch.Tensor], device, parts=ALL_PARTS,
+                 op_dtype: torch.dtype = torch.bfloat16):
+        """`parts`: which sections of the state_dict are laid out for the kernels -- the whole model for
+        the pipeline; a single section when one of the reference's sub-modules (renderformer.layers.*,
+        ViewTransformer, DPTHead) is called on its own (renderformer_b200/modules.py).
+        `op_dtype`: tensor-core operand format of the two transformer stacks, torch.bfloat16 or torch.float16
+        (same tcgen05 rate; fp16 has 3 more mantissa bits: ~8x less rounding noise).  Token
+        encoders and the DPT head always use fp16 operands."""
         cfg.check_supported()
+        if op_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("op_dtype must be torch.bfloat16 or torch.float16")
         self.cfg = cfg
+        self.op = op_dtype
+        self.parts = tuple(parts)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.RfbError("renderformer_b200.Engine needs a CUDA device (there is no CPU fallback)")
@@ -122,7 +136,7 @@ class Engine:
     # ------------------------------------------------------------------ weights
     def _prepare(self, sd: Dict[str, torch.Tensor]) -> None:
         cfg, dev = self.cfg, self.device
-        bf, hf = torch.bfloat16, torch.float16
+        bf, hf = self.op, torch.float16
 
         def g(k):
             return sd[k].detach().to(dev, torch.float32)
@@ -145,6 +159,20 @@ class Engine:
         fused_dec = self.fused_dec
 
         d = cfg.latent_dim
+        if "tokens" in self.parts:
+            self._prepare_tokens(g, put, d)
+        if "ray" in self.parts:
+            self._prepare_ray(g, put)
+        if "encoder" in self.parts:
+            self._prepare_encoder(g, put, fold, swiglu_w)
+        if "decoder" in self.parts:
+            self._prepare_decoder(g, put, fold, swiglu_w)
+        if "dpt" in self.parts:
+            self._prepare_dpt(g, put, conv_w)
+
+    def _prepare_tokens(self, g, put, d):
+        cfg, dev = self.cfg, self.device
+        hf = torch.float16
         put("tri_token", g("tri_token").reshape(-1))
         put("reg_tokens", g("reg_tokens").reshape(cfg.num_register_tokens, d))
         vw = g("vn_encoding_proj.weight")
@@ -164,6 +192,17 @@ class Engine:
         wrp[:, :C_] = wr
         put("tex.wr", wrp, hf)
         put("tex.norm", g("texture_encoder_norm.weight"))
+
+    def _prepare_ray(self, g, put):
+        hf = torch.float16
+        v = "view_transformer."
+        put("ray.token", g(v + "ray_map_patch_token").reshape(-1))
+        put("ray.w", g(v + "ray_map_encoder.weight"), hf), put("ray.b", g(v + "ray_map_encoder.bias"))
+        put("ray.norm", g(v + "ray_map_encoder_norm.weight"))
+
+    def _prepare_encoder(self, g, put, fold, swiglu_w):
+        cfg = self.cfg
+        bf = self.op
         put("enc.freqs", g("transformer.rope_emb.freqs"))
         for i in range(cfg.num_layers):
             p, o = f"transformer.layers.{i}.", f"enc{i}."
@@ -174,11 +213,12 @@ class Engine:
             put(o + "w13", fold(swiglu_w(p + "ffn."), p + "ffn_norm.weight"), bf)
             put(o + "w2", g(p + "ffn.w2.weight"), bf)
 
+    def _prepare_decoder(self, g, put, fold, swiglu_w):
+        cfg = self.cfg
+        bf = self.op
+        fused_dec = self.fused_dec
         v = "view_transformer."
         dv = cfg.view_transformer_latent_dim
-        put("ray.token", g(v + "ray_map_patch_token").reshape(-1))
-        put("ray.w", g(v + "ray_map_encoder.weight"), hf), put("ray.b", g(v + "ray_map_encoder.bias"))
-        put("ray.norm", g(v + "ray_map_encoder_norm.weight"))
         put("dec.freqs", g(v + "transformer.rope_emb.freqs"))
         for i in range(cfg.view_transformer_n_layers):
             p, o = v + f"transformer.layers.{i}.", f"dec{i}."
@@ -204,7 +244,9 @@ class Engine:
         put("dec.wkv_all", torch.cat([self.w.pop(f"dec{i}.wk") for i in range(Lv)] +
                                      [self.w.pop(f"dec{i}.wv") for i in range(Lv)], dim=0))
 
-        h = v + "out_dpt."
+    def _prepare_dpt(self, g, put, conv_w):
+        hf = torch.float16
+        h = "view_transformer.out_dpt."
         for i in range(4):
             put(f"dpt.proj{i}.w", g(h + f"projects.{i}.weight").flatten(1), hf)
             put(f"dpt.proj{i}.b", g(h + f"projects.{i}.bias"))
@@ -231,8 +273,8 @@ class Engine:
     # ------------------------------------------------------------------ shared blocks
     def _ffn(self, x, rows, d, n_w, w13, w2):
         """x += w2(silu(w1 n(x)) * w3 n(x))   layers/attention.py:56-57,526."""
-        h = ops.rmsnorm(x, n_w, self._e((rows, d), torch.bfloat16), rows=rows, d=d, eps=EPS)
-        g = ops.gemm(h, w13, epi=L.EPI_SWIGLU, out_dtype=torch.bfloat16)
+        h = ops.rmsnorm(x, n_w, self._e((rows, d), self.op), rows=rows, d=d, eps=EPS)
+        g = ops.gemm(h, w13, epi=L.EPI_SWIGLU, out_dtype=self.op)
         ops.gemm(g, w2, out=x, res1=x)
 
     # ------------------------------------------------------------------ stage 1
@@ -253,8 +295,17 @@ class Engine:
                 return sts[0]
             cat = [torch.cat(ts, dim=0) for ts in zip(*(st.tensors() for st in sts))]
             return SceneState(B, sts[0].N, sts[0].Nt, sts[0].Ntp, *cat, sts[0].dv)
+        x, pos, bits, words, (B, N, Nt, Ntp), tri, mask_u8 = self.construct_seq(triangles, texture, mask, vn, texture_is_log)
+        return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8, taps)
+
+    def construct_seq(self, triangles, texture, mask, vn, texture_is_log: bool = False):
+        """RenderFormer.construct_seq + process_tri_vpos_list (models/renderformer.py:103-169): token rows
+        x fp32 [B*Ntp, d] (16 register tokens, then tri_token + RMSNorm(texture emb) + RMSNorm(normal emb);
+        rows padded to a multiple of 8 with zeros), RoPE positions pos [B, Ntp, 9] (masked centroid for the
+        register rows), packed key mask bits [B, words]."""
+        cfg, w, dev = self.cfg, self.w, self.device
         B, N = triangles.shape[:2]
-        d, H = cfg.latent_dim, cfg.num_heads
+        d = cfg.latent_dim
         nreg = cfg.num_register_tokens
         Nt, Ntp = N + nreg, _rup(N + nreg, 8)
         tri = triangles.reshape(B, N, 9).to(dev, torch.float32).contiguous()
@@ -264,7 +315,6 @@ class Engine:
         mask_u8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8)
         C_, P = cfg.texture_channels, cfg.texture_encode_patch_size
 
-        # token construction  (models/renderformer.py:126-169)
         log_ch = 0 if (cfg.use_ldr or texture_is_log) else 3
         if const_tex:
             if tex.shape[2] != C_:
@@ -288,17 +338,24 @@ class Engine:
             ops.positions(tri[b], mask_u8[b], None, pos[b], n=N, n_reg=nreg, rows_out=Ntp, n_views=1)
         words = 4 * ((Ntp + 127) // 128)
         bits = ops.pack_mask(mask_u8, self._e((B, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=B)
-
-        return self._encode_fused(x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8, taps)
+        return x, pos, bits, words, (B, N, Nt, Ntp), tri, mask_u8
 
     def _encode_fused(self, x, pos, bits, words, B, N, Nt, Ntp, tri, mask_u8, taps=None) -> SceneState:
-        """Encoder + K/V hoist with RMSNorm fused into the GEMMs.  State carried between GEMMs:
-        x (fp32 residual), xb (bf16 copy of x), xsq (per-row partial sums of squares of x, one per
-        128 columns)."""
+        """Encoder + K/V hoist with RMSNorm fused into the GEMMs."""
+        x, xb, xsq = self.encoder_layers(x, pos, bits, words, B, Ntp, taps)
+        k_all, v_all = self.hoist_kv(xb, xsq, B, Ntp)
+        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, self.cfg.latent_dim), tri, mask_u8, bits, k_all, v_all,
+                          self.cfg.view_transformer_latent_dim)
+
+    def encoder_layers(self, x, pos, bits, words, B, Ntp, taps=None):
+        """TransformerEncoder.forward (layers/attention.py:579-590) on x fp32 [B*Ntp, d] (updated in place),
+        pos [B, Ntp, 9], packed key mask `bits` [B, words].  State carried between GEMMs: x (fp32 residual),
+        xb (bf16 copy of x), xsq (per-row partial sums of squares of x, one per 128 columns); returns all
+        three."""
         cfg, w = self.cfg, self.w
-        d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
+        d, H = cfg.latent_dim, cfg.num_heads
         rows = B * Ntp
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = self.op, torch.float32
         nrm = dict(norm_dim=d, norm_eps=EPS)
         P = d // 128
         xb, xsq = self._e((rows, d), bf), self._e((rows, P), f32)
@@ -322,13 +379,39 @@ class Engine:
             ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
             if taps is not None:
                 taps["enc_stream"].append((xb.clone(), xsq.clone()))
-        # hoisted decoder K / V projections of the triangle tokens for ALL layers in two GEMMs
-        # (view independent, SURVEY E5; every layer's kv_norm weight is folded into its rows)
-        Lv = cfg.view_transformer_n_layers
-        v_all = self._e((B, Lv * dv, Ntp), bf)
-        k_all = ops.gemm(xb, w["dec.wkv_all"], out=self._e((rows, Lv * dv), f32), in_sumsq=xsq, vt_out=v_all,
-                         vt_split=Lv * dv, vt_rows_per_batch=Ntp, **nrm).view(B, Ntp, Lv * dv)
-        return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, d), tri, mask_u8, bits, k_all, v_all, dv)
+        return x, xb, xsq
+
+    def hoist_kv(self, xb, xsq, B, Ntp):
+        """Decoder K / V projections of the triangle tokens for ALL layers in one GEMM (view independent,
+        SURVEY E5; every layer's kv_norm weight is folded into its rows): k_all fp32 [B, Ntp, L*dv]
+        (pre-QK-norm, pre-RoPE), v_all bf16 [B, L*dv, Ntp] (transposed)."""
+        cfg, w = self.cfg, self.w
+        d, dv, Lv = cfg.latent_dim, cfg.view_transformer_latent_dim, cfg.view_transformer_n_layers
+        v_all = self._e((B, Lv * dv, Ntp), self.op)
+        k_all = ops.gemm(xb, w["dec.wkv_all"], out=self._e((B * Ntp, Lv * dv), torch.float32), in_sumsq=xsq,
+                         vt_out=v_all, vt_split=Lv * dv, vt_rows_per_batch=Ntp, norm_dim=d, norm_eps=EPS)
+        return k_all.view(B, Ntp, Lv * dv), v_all
+
+    def scene_state_from_tokens(self, seq, tri_pos_world, mask) -> SceneState:
+        """SceneState from ready-made encoder output `seq` [B, Nt, d] (ViewTransformer / TransformerDecoder
+        called on their own, models/view_transformer.py:88): rows are padded to a multiple of 8, the decoder
+        K / V are hoisted.  `mask` [B, Nt] bool over ALL tokens (register prefix included)."""
+        cfg = self.cfg
+        B, Nt, d = seq.shape
+        Ntp = _rup(Nt, 8)
+        dev = self.device
+        x = torch.zeros((B, Ntp, d), dtype=torch.float32, device=dev)
+        x[:, :Nt] = seq.to(dev, torch.float32)
+        P = d // 128
+        xb, xsq = self._e((B * Ntp, d), self.op), self._e((B * Ntp, P), torch.float32)
+        ops.rowstat(x.view(B * Ntp, d), xb, xsq, rows=B * Ntp, d=d)
+        k_all, v_all = self.hoist_kv(xb, xsq, B, Ntp)
+        m8 = mask.to(dev).contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(dev, torch.uint8)
+        words = 4 * ((Ntp + 127) // 128)
+        bits = ops.pack_mask(m8, self._e((B, words), torch.int32), n=Nt, n_prefix=0, words=words, batch=B)
+        nreg = cfg.num_register_tokens
+        return SceneState(B, Nt - nreg, Nt, Ntp, x, None, m8[:, nreg:].contiguous(), bits, k_all, v_all,
+                          cfg.view_transformer_latent_dim)
 
     def own_triangles(self, N: int, sh: RowShard):
         """[t0, t1): the triangles whose token rows rank `sh.rank` owns."""
@@ -350,7 +433,7 @@ class Engine:
         d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
         nreg = cfg.num_register_tokens
         Nt, Ntp = N + nreg, _rup(N + nreg, 8)
-        bf, f32, hf = torch.bfloat16, torch.float32, torch.float16
+        bf, f32, hf = self.op, torch.float32, torch.float16
         S = sh.shard_rows(Ntp)
         r0, r1 = sh.my_rows(Ntp)
         rows = r1 - r0
@@ -424,10 +507,7 @@ class Engine:
             sh.all_gather(xbs, chunk)
         # hoisted decoder K / V of ALL layers from the gathered stream, replicated on every rank (0.2 TFLOP:
         # cheaper than moving the 300 MB result over NVLink)
-        Lv = cfg.view_transformer_n_layers
-        v_all = self._e((1, Lv * dv, Ntp), bf)
-        k_all = ops.gemm(xb_all, w["dec.wkv_all"], out=self._e((Ntp, Lv * dv), f32), in_sumsq=xsq_all, vt_out=v_all,
-                         vt_split=Lv * dv, vt_rows_per_batch=Ntp, **nrm).view(1, Ntp, Lv * dv)
+        k_all, v_all = self.hoist_kv(xb_all, xsq_all, 1, Ntp)
         # the fp32 token sequence itself (API completeness / tests): one more gather
         seq = self._e((sh.world * S, d), f32)
         if rows > 0:
@@ -445,7 +525,7 @@ class Engine:
         Lv = cfg.view_transformer_n_layers
         return SceneState(B, N, Nt, Ntp, self._e((B, Ntp, d), torch.float32), self._e((B, N, 9), torch.float32),
                           self._e((B, N), torch.uint8), self._e((B, words), torch.int32),
-                          self._e((B, Ntp, Lv * dv), torch.float32), self._e((B, Lv * dv, Ntp), torch.bfloat16), dv)
+                          self._e((B, Ntp, Lv * dv), torch.float32), self._e((B, Lv * dv, Ntp), self.op), dv)
 
     # ------------------------------------------------------------------ stage 2
     def _keys_all_layers(self, st: SceneState, b: int, pos, V: int) -> torch.Tensor:
@@ -453,7 +533,7 @@ class Engine:
         views in one launch: bf16 [V*Ntp, L*dv]; layer i is the column slice [i*dv, (i+1)*dv)."""
         cfg = self.cfg
         dv, Lv = cfg.view_transformer_latent_dim, cfg.view_transformer_n_layers
-        kall = self._e((V * st.Ntp, Lv * dv), torch.bfloat16)
+        kall = self._e((V * st.Ntp, Lv * dv), self.op)
         ops.qknorm_rope(st.k_all[b], self.w["dec.kn_all"], kall, rows=V * st.Ntp, d=dv, nseg=Lv, ldx=Lv * dv,
                         ldo=Lv * dv, in_period=st.Ntp, pos=pos, freqs=self.w["dec.freqs"], eps=EPS)
         return kall
@@ -473,47 +553,77 @@ class Engine:
     @torch.no_grad()
     def render_views(self, st: SceneState, b: int, c2w: Optional[torch.Tensor], fov_deg: Optional[torch.Tensor],
                      resolution: int, taps: Optional[dict] = None, rays_d: Optional[torch.Tensor] = None,
-                     tri_cam: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     tri_cam: Optional[torch.Tensor] = None, pos_cam: Optional[torch.Tensor] = None,
+                     raw_log: bool = False) -> torch.Tensor:
         """Render V views of scene `b` -> HDR fp32 [V,R,R,3].  Either cameras (c2w [V,4,4], fov_deg [V] or
         [V,1]; rays and camera-space triangles are derived on the device) or, for the model-level entry
         (models/renderformer.py:171-206), an explicit camera-space ray map `rays_d` [V,R,R,3] together
-        with the camera-space triangles `tri_cam` [V,N,9]."""
-        cfg, w, dev = self.cfg, self.w, self.device
+        with the camera-space triangles `tri_cam` [V,N,9] -- or the ready RoPE positions `pos_cam`
+        [V,Nt,9] (register centroids included) as ViewTransformer.forward receives them
+        (models/view_transformer.py:88).  `raw_log`: return the head's pre-ELU output [V,R,R,3] instead
+        (DPTHead.forward, layers/dpt.py:242-273)."""
+        cfg, dev = self.cfg, self.device
         explicit = rays_d is not None
-        if explicit and tri_cam is None:
-            raise ValueError("rays_d needs tri_cam (camera-space triangle vertices)")
+        if explicit and tri_cam is None and pos_cam is None:
+            raise ValueError("rays_d needs tri_cam (camera-space triangle vertices) or pos_cam")
         V, R = (rays_d.shape[0] if explicit else c2w.shape[0]), resolution
         if R % 64 != 0 and cfg.view_transformer_use_swin_attn:
             raise ValueError("resolution must be a multiple of 64 for swin attention")  # SURVEY §8b
         if R % 8 != 0:
             raise ValueError("resolution must be a multiple of the 8-pixel patch size")
         Hp = Wp = R // 8
-        Nr = Hp * Wp
-        dv, Hh = cfg.view_transformer_latent_dim, cfg.view_transformer_n_heads
         Ntp, N = st.Ntp, st.N
-        rows = V * Nr
-        bf = torch.bfloat16
         if explicit:
             rays = rays_d.to(dev, torch.float32).contiguous()
-            tc = tri_cam.reshape(V, N, 9).to(dev, torch.float32).contiguous()
-            pos = self._e((V, Ntp, 9), torch.float32)
-            for vi in range(V):  # centroid registers + vertices, already in camera space
-                ops.positions(tc[vi], st.mask_u8[b], None, pos[vi], n=N, n_reg=cfg.num_register_tokens, rows_out=Ntp,
-                              n_views=1)
-            rt = ops.ray_map_tokens(rays, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
+            if pos_cam is not None:
+                pos = torch.zeros((V, Ntp, 9), dtype=torch.float32, device=dev)
+                pos[:, :pos_cam.shape[1]] = pos_cam.to(dev, torch.float32)
+            else:
+                tc = tri_cam.reshape(V, N, 9).to(dev, torch.float32).contiguous()
+                pos = self._e((V, Ntp, 9), torch.float32)
+                for vi in range(V):  # centroid registers + vertices, already in camera space
+                    ops.positions(tc[vi], st.mask_u8[b], None, pos[vi], n=N, n_reg=cfg.num_register_tokens,
+                                  rows_out=Ntp, n_views=1)
+            x = self.ray_tokens(V, R, rays=rays)
         else:
             c2w = c2w.to(dev, torch.float32).contiguous()
             fov = fov_deg.reshape(-1).to(dev, torch.float32).contiguous()
             pos = ops.positions(st.tri[b], st.mask_u8[b], c2w, self._e((V, Ntp, 9), torch.float32), n=N,
                                 n_reg=cfg.num_register_tokens, rows_out=Ntp, n_views=V)
-            rt = ops.ray_tokens(fov, self._e((rows, 192), torch.float16), n_views=V, resolution=R)
+            x = self.ray_tokens(V, R, fov=fov)
+        feats = self.decoder_layers(st, b, x, pos, V, Hp, Wp, taps)
+        return self._dpt(feats, V, Hp, Wp, raw_out=raw_log)
+
+    def ray_tokens(self, V: int, R: int, fov=None, rays=None):
+        """Ray-bundle patch tokens x fp32 [V*(R/8)^2, dv]: pinhole rays (utils/ray_generator.py:13-50) or an
+        explicit ray map -> 8x8 patches -> ray_map_patch_token + RMSNorm(Linear)  (view_transformer.py:104-108)."""
+        w = self.w
+        dv = self.cfg.view_transformer_latent_dim
+        rows = V * (R // 8) ** 2
+        rt = self._e((rows, 192), torch.float16)
+        if rays is not None:
+            ops.ray_map_tokens(rays, rt, n_views=V, resolution=R)
+        else:
+            ops.ray_tokens(fov, rt, n_views=V, resolution=R)
         lin = ops.gemm(rt, w["ray.w"], bias=w["ray.b"], out_dtype=torch.float32)
         x = self._e((rows, dv), torch.float32)
         ops.token_assemble(lin, w["ray.norm"], None, None, w["ray.token"], None, x, n_prefix=0, rows_in=rows,
                            rows_out=rows, batch=1, d=dv)
-        words = st.mask_bits.shape[1]
+        return x
+
+    def decoder_layers(self, st: SceneState, b: int, x, pos, V, Hp, Wp, taps=None, out_layers=None, want_f32=False):
+        """TransformerDecoder.forward (layers/attention.py:673-688) for V views of scene `b`: x fp32
+        [V*Hp*Wp, dv] ray tokens (updated in place), pos [V, Ntp, 9] camera-space RoPE positions of the
+        triangle tokens.  Returns the feature maps of `out_layers` (default: the four DPT taps) as fp16
+        [rows, dv] tensors (fp32 clones with `want_f32`)."""
+        cfg, w = self.cfg, self.w
+        out_layers = list(cfg.out_layers) if out_layers is None else list(out_layers)
         if self.fused_dec:
-            return self._decode_fused(st, b, x, pos, V, Hp, Wp, taps)
+            return self._decode_fused(st, b, x, pos, V, Hp, Wp, taps, out_layers, want_f32)
+        dv, Hh = cfg.view_transformer_latent_dim, cfg.view_transformer_n_heads
+        Nr, Ntp = Hp * Wp, st.Ntp
+        rows = V * Nr
+        bf = self.op
         feats = []
         Lv = cfg.view_transformer_n_layers
         kall = self._keys_all_layers(st, b, pos, V)
@@ -543,13 +653,13 @@ class Engine:
                           ldo=dv, q_bs=Nr * 2 * dv, k_bs=Nr * 2 * dv, vt_bs=dv * Nrp, o_bs=Nr * dv)
             ops.gemm(att, w[o + "s.wo"], out=x, res1=x)
             self._ffn(x, rows, dv, w[o + "n_f"], w[o + "w13"], w[o + "w2"])
-            if i in cfg.out_layers:
-                feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
+            if i in out_layers:
+                feats.append(x.clone() if want_f32 else ops.cast(x, self._e((rows, dv), torch.float16)))
                 if taps is not None:
                     taps.setdefault("dec_feats", []).append(x.clone().view(V, Nr, dv))
-        return self._dpt(feats, V, Hp, Wp)
+        return feats
 
-    def _decode_fused(self, st: SceneState, b: int, x, pos, V, Hp, Wp, taps):
+    def _decode_fused(self, st: SceneState, b: int, x, pos, V, Hp, Wp, taps, out_layers, want_f32=False):
         """Swin decoder with RMSNorm / QK-RMSNorm fused into the GEMMs and the attention kernels.
         Carried state: x fp32 (token order), xb bf16 copy + xsq partial row sums (token order), and
         their window-order twins xbw / xsqw written by the cross-attention out-projection."""
@@ -557,7 +667,7 @@ class Engine:
         dv, Hh = cfg.view_transformer_latent_dim, cfg.view_transformer_n_heads
         Nr, Ntp = Hp * Wp, st.Ntp
         rows = V * Nr
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = self.op, torch.float32
         nrm = dict(norm_dim=dv, norm_eps=EPS)
         P = dv // 128
         xb, xsq = self._e((rows, dv), bf), self._e((rows, P), f32)
@@ -590,11 +700,11 @@ class Engine:
             # SwiGLU
             g = ops.gemm(xb, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq, **nrm)
             ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
-            if i in cfg.out_layers:
-                feats.append(ops.cast(x, self._e((rows, dv), torch.float16)))
+            if i in out_layers:
+                feats.append(x.clone() if want_f32 else ops.cast(x, self._e((rows, dv), torch.float16)))
                 if taps is not None:
                     taps.setdefault("dec_feats", []).append(x.clone().view(V, Nr, dv))
-        return self._dpt(feats, V, Hp, Wp)
+        return feats
 
     # ------------------------------------------------------------------ DPT head (layers/dpt.py:242-273)
     def _conv(self, x, name, B, H, W, Cin, **kw):
@@ -626,7 +736,10 @@ class Engine:
         o = ops.gemm(o, self.w[name + "out.w"], bias=self.w[name + "out.b"], out=self._e((B * H * W, F_), hf))
         return ops.upsample_bilinear(o, self._e((B * Ho * Wo, F_), hf), B=B, Hi=H, Wi=W, Ho=Ho, Wo=Wo, C_=F_)
 
-    def _dpt(self, feats, V, Hp, Wp):
+    def _dpt(self, feats, V, Hp, Wp, raw_out: bool = False):
+        """DPTHead.forward (layers/dpt.py:242-273) on four fp16 feature maps [V*Hp*Wp, dv] -> HDR image fp32
+        [V, 8Hp, 8Wp, 3] (the head's ELU and the pipeline's 10^x - 1 are the last conv's epilogue), or with
+        `raw_out` the head's own output before the ELU."""
         cfg, w = self.cfg, self.w
         hf = torch.float16
         C = list(cfg.dpt_out_channels)
@@ -657,6 +770,6 @@ class Engine:
         # head (layers/dpt.py:266-271); F.interpolate to (8*Hp, 8*Wp) is the identity here (E2)
         o1 = self._conv(p1, "dpt.oc1", V, Ho, Wo, F_, bias=w["dpt.oc1.b"], out=self._e((V * Ho * Wo, F_ // 2), hf))
         img = self._e((V, Ho, Wo, 3), torch.float32)
-        self._conv(o1, "dpt.oc2", V, Ho, Wo, F_ // 2, bias=w["dpt.oc2.b"], epi=L.EPI_FINAL, w2=w["dpt.oc3.w"],
-                   b2=w["dpt.oc3.b"], out=img, ldo=3)
+        self._conv(o1, "dpt.oc2", V, Ho, Wo, F_ // 2, bias=w["dpt.oc2.b"], epi=L.EPI_FINAL_RAW if raw_out else L.EPI_FINAL,
+                   w2=w["dpt.oc3.w"], b2=w["dpt.oc3.b"], out=img, ldo=3)
         return img

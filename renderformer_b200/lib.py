@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "librfb200.so")
 
 F32, BF16, F16 = 0, 1, 2
 A_LINEAR, A_CONV3X3 = 0, 1
-EPI_STORE, EPI_SWIGLU, EPI_FINAL = 0, 1, 2
+EPI_STORE, EPI_SWIGLU, EPI_FINAL, EPI_FINAL_RAW = 0, 1, 2, 3
 
 _ERRORS = {-1: "bad argument / unsupported shape", -2: "misaligned pointer or stride",
            -3: "CUDA driver entry point unavailable", -4: "tensor map rejected", -5: "kernel launch failed"}
@@ -61,13 +61,14 @@ class AttnArgs(C.Structure):
         ("q_sumsq", C.c_void_p), ("k_sumsq", C.c_void_p), ("sumsq_ld", C.c_int), ("sumsq_parts", C.c_int),
         ("norm_dim", C.c_int),
         ("norm_eps", C.c_float),
+        ("dtype", C.c_int),
     ]
 
 
 # every symbol include/rfb200.h declares (tests/test_abi.py checks the built library exports them)
 SYMBOLS = [
-    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope",
-    "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_ray_map_tokens", "rfb_positions",
+    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope", "rfb_qknorm_rope_table",
+    "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_ray_map_tokens", "rfb_ray_map", "rfb_positions",
     "rfb_pack_mask", "rfb_cast", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear", "rfb_ldr_quantize",
 ]
 
@@ -90,13 +91,15 @@ def load() -> C.CDLL:
         "rfb_gemm": [C.POINTER(GemmArgs), p],
         "rfb_attention": [C.POINTER(AttnArgs), p],
         "rfb_rmsnorm": [p, ll, p, p, i, ll, i, i, f, p, p],
-        "rfb_rowstat": [p, p, i, ll, p, i, i, i, i, p],
-        "rfb_qknorm_rope": [p, ll, i, p, p, ll, i, i, i, f, p, p, i, p],
+        "rfb_rowstat": [p, p, i, ll, p, i, i, i, i, p, p],
+        "rfb_qknorm_rope_table": [p, ll, p, p, i, ll, i, i, i, f, p, p, ll, p],
+        "rfb_qknorm_rope": [p, ll, i, p, p, i, ll, i, i, i, f, p, p, i, p],
         "rfb_token_assemble": [p, p, p, p, p, p, i, p, i, i, i, i, p],
         "rfb_texture_prep": [p, p, ll, i, i, i, p],
         "rfb_texture_const_prep": [p, p, ll, i, i, i, p],
         "rfb_ldr_quantize": [p, p, ll, i, p],
         "rfb_ray_map_tokens": [p, p, i, i, p],
+        "rfb_ray_map": [p, p, p, i, i, p],
         "rfb_vn_encode": [p, p, i, i, i, p],
         "rfb_ray_tokens": [p, p, i, i, p],
         "rfb_positions": [p, p, p, p, i, i, i, i, p],

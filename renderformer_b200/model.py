@@ -17,32 +17,41 @@ from torch import nn
 from .config import RenderFormerConfig
 from . import lib as L
 from .engine import Engine, SceneState
-from .synth import state_dict_shapes
 
 
-class _Params(nn.Module):
-    """A parameter container addressed by dotted state_dict keys."""
+class RenderFormer(nn.Module):
+    """models/renderformer.py:13-206.  The parameter tree is composed of the same sub-modules as the
+    reference (renderformer_b200/modules.py: TransformerEncoder, ViewTransformer -> TransformerDecoder +
+    DPTHead, ...), so attribute paths and state_dict keys are the reference's; `forward` runs the fused
+    engine over the whole tree instead of calling the sub-modules one by one."""
 
-    def add(self, dotted: str, shape, trainable: bool = True) -> None:
-        mod = self
-        *path, leaf = dotted.split(".")
-        for name in path:
-            if name not in mod._modules:
-                mod.add_module(name, _Params())
-            mod = mod._modules[name]
-        mod.register_parameter(leaf, nn.Parameter(torch.zeros(shape), requires_grad=trainable))
-
-
-class RenderFormer(_Params):
     def __init__(self, config: RenderFormerConfig):
         super().__init__()
         if isinstance(config, dict):
             config = RenderFormerConfig.from_dict(config)
+        config.check_supported()
         self.config = config
-        for key, shape in state_dict_shapes(config).items():
-            self.add(key, shape, trainable=not key.endswith("rope_emb.freqs"))
-        self._engine: Optional[Engine] = None
-        self._engine_key = None
+        from .modules import NeRFEncoding, TransformerEncoder, ViewTransformer
+        d = config.latent_dim
+        with torch.device("meta"):  # no throw-away initialisation of 0.2-0.5 G parameters
+            self.rope_dim = config.vertex_pe_num_freqs
+            self.vn_pe = NeRFEncoding(in_dim=9, num_frequencies=config.vn_pe_num_freqs, include_input=True)
+            self.vn_encoding_proj = nn.Linear(self.vn_pe.get_out_dim(), d)
+            self.vn_encoder_norm = nn.RMSNorm(d)
+            self.texture_encoder = nn.Linear(config.texture_channels * config.texture_encode_patch_size ** 2, d)
+            self.texture_encoder_norm = nn.RMSNorm(d)
+            self.tri_token = nn.Parameter(torch.randn(1, 1, d))
+            self.reg_tokens = nn.Parameter(torch.randn(1, config.num_register_tokens, d))
+            self.skip_token_num = config.num_register_tokens
+            self.transformer = TransformerEncoder(
+                num_layers=config.num_layers, num_heads=config.num_heads, hidden_dim=d,
+                ffn_hidden_dim=config.dim_feedforward, dropout=config.dropout, activation=config.activation,
+                norm_type=config.norm_type, norm_first=config.norm_first, rope_dim=self.rope_dim,
+                rope_type=config.rope_type, bias=config.bias, qk_norm=config.view_indep_qk_norm,
+                rope_double_max_freq=config.rope_double_max_freq)
+            self.view_transformer = ViewTransformer(config)
+        self.to_empty(device="cpu")
+        self._engines: Dict[torch.dtype, tuple] = {}
         self.reset_parameters()
 
     def reset_parameters(self, seed: int = 0) -> None:
@@ -76,17 +85,44 @@ class RenderFormer(_Params):
         return next(self.parameters()).device
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        self._engine = None
+        self._engines = {}
         return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
+    # ---- the reference's helper methods, on the kernels ------------------------------
+    @torch.no_grad()
+    def process_tri_vpos_list(self, tri_vpos_list, valid_mask):
+        """models/renderformer.py:103-124: prepend `num_register_tokens` copies of the masked vertex
+        centroid to the positions and True to the mask (rfb_positions)."""
+        from . import ops
+        B, N = tri_vpos_list.shape[:2]
+        nreg = self.config.num_register_tokens
+        dev = tri_vpos_list.device
+        tri = tri_vpos_list.reshape(B, N, 9).to(torch.float32).contiguous()
+        m8 = valid_mask.contiguous().view(torch.uint8) if valid_mask.dtype == torch.bool else valid_mask.to(torch.uint8)
+        pos = torch.empty((B, N + nreg, 9), dtype=torch.float32, device=dev)
+        for b in range(B):
+            ops.positions(tri[b], m8[b], None, pos[b:b + 1], n=N, n_reg=nreg, rows_out=N + nreg, n_views=1)
+        pad = torch.ones((B, nreg), dtype=valid_mask.dtype, device=dev)
+        return pos, torch.cat([pad, valid_mask], dim=1)
+
+    @torch.no_grad()
+    def construct_seq(self, tri_vpos_list, texture_patch_list, valid_mask, vns):
+        """models/renderformer.py:126-169 -> (seq [B, Nt, d], padded mask [B, Nt], positions [B, Nt, 9]);
+        `texture_patch_list` with the emission channels already log-encoded, as in the reference."""
+        eng = self.engine()
+        x, pos, _bits, _words, (B, N, Nt, Ntp), _tri, _m8 = eng.construct_seq(tri_vpos_list, texture_patch_list,
+                                                                               valid_mask, vns, texture_is_log=True)
+        pad = torch.ones((B, self.config.num_register_tokens), dtype=valid_mask.dtype, device=x.device)
+        return (x.view(B, Ntp, -1)[:, :Nt], torch.cat([pad, valid_mask.to(x.device)], dim=1), pos[:, :Nt])
+
     # ---- engine -------------------------------------------------------------------
-    def engine(self) -> Engine:
-        """Kernel-ready weight layouts, cached per (device, parameter versions)."""
+    def engine(self, op_dtype: torch.dtype = torch.bfloat16) -> Engine:
+        """Kernel-ready weight layouts, cached per operand format and (device, parameter versions)."""
         key = (str(self.device), tuple(p._version for p in self.parameters()))
-        if self._engine is None or self._engine_key != key:
-            self._engine = Engine(self.config, self.state_dict(), self.device)
-            self._engine_key = key
-        return self._engine
+        hit = self._engines.get(op_dtype)
+        if hit is None or hit[0] != key:
+            self._engines[op_dtype] = hit = (key, Engine(self.config, self.state_dict(), self.device, op_dtype=op_dtype))
+        return hit[1]
 
     @torch.no_grad()
     def forward(self, tri_vpos_list, texture_patch_list, valid_mask, vns, rays_o=None, rays_d=None,
@@ -98,13 +134,14 @@ class RenderFormer(_Params):
         map, tri_vpos_view_tf [B,V,N,9] camera-space vertices.  Returns log-encoded images
         [B, V, 3, H, W] like the reference.  Alternatively pass cameras as keywords (`c2w` [B,V,4,4],
         `fov` [B,V,1] degrees, `resolution`) and leave rays_d / tri_vpos_view_tf None.  `tf32_view_tf`
-        is accepted and ignored (one precision policy).  The pipeline calls the engine
+        is accepted and ignored; the operand format follows the ambient `torch.autocast("cuda", dtype)` like
+        the reference's (fp16 outside an autocast region).  The pipeline calls the engine
         directly and skips the log round trip."""
         if rays_o is not None and bool((rays_o != 0).any()):
             # the reference rotates the queries with RoPE at ray_pos = rays_o (view_transformer.py:109,
             # attention.py:668-671); this engine hard-wires the camera-space identity (origin 0)
             raise ValueError("RenderFormer.forward: rays_o must be 0 (camera-space rays, as the pipeline passes them)")
-        eng = self.engine()
+        eng = self.engine(operand_dtype(torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16))
         st = eng.encode_scene(tri_vpos_list, texture_patch_list, valid_mask, vns, texture_is_log=True)
         if rays_d is not None and tri_vpos_view_tf is not None:
             B, V, R = rays_d.shape[0], rays_d.shape[1], rays_d.shape[2]
@@ -118,6 +155,24 @@ class RenderFormer(_Params):
                              "or the c2w / fov / resolution keywords")
         hdr = torch.stack(out, dim=0)  # [B,V,H,W,3]
         return torch.log10(hdr + 1.0).permute(0, 1, 4, 2, 3)
+
+
+_warned_fp32 = [False]
+
+
+def operand_dtype(torch_dtype: torch.dtype) -> torch.dtype:
+    """Tensor-core operand format for a requested `torch_dtype` (rendering_pipeline.py:98 accepts bfloat16,
+    float16, float32): float16 -> fp16 operands, bfloat16 -> bf16 operands; float32 has no tensor-core format
+    on this path and maps to fp16 operands with fp32 accumulation -- the most precise available (~1e-3
+    class error on HDR pixels) -- with a one-time warning."""
+    assert torch_dtype in (torch.bfloat16, torch.float16, torch.float32), \
+        f"Invalid precision: {torch_dtype}\nChoose from: torch.bfloat16, torch.float16, torch.float32"
+    if torch_dtype == torch.float32 and not _warned_fp32[0]:
+        import warnings
+        warnings.warn("renderformer_b200: torch_dtype=float32 runs with fp16 tensor-core operands and fp32 accumulation "
+                      "(there is no fp32 tensor-core path); expect ~1e-3 relative error on HDR pixels")
+        _warned_fp32[0] = True
+    return torch.bfloat16 if torch_dtype == torch.bfloat16 else torch.float16
 
 
 class RenderFormerRenderingPipeline:
@@ -158,12 +213,13 @@ class RenderFormerRenderingPipeline:
         self.model.to(device)
 
     @torch.no_grad()
-    def encode(self, triangles, texture, mask, vn, shard=None, texture_own_rows: bool = False) -> SceneState:
+    def encode(self, triangles, texture, mask, vn, shard=None, texture_own_rows: bool = False,
+               torch_dtype: torch.dtype = torch.float16) -> SceneState:
         """View-independent stage only (exposed for multi-GPU view sharding).  With `cuda_graphs` the
         returned SceneState is the graph's static output (overwritten by the next call of that shape).
         `shard` (engine.RowShard, see renderformer_b200.dist.row_shard) splits the token rows of the
         stage over the ranks; every rank passes the same scene and gets the complete state."""
-        eng = self.model.engine()
+        eng = self.model.engine(operand_dtype(torch_dtype))
         inputs = (triangles, texture, mask, vn)
         kw = dict(shard=shard, texture_own_rows=texture_own_rows)
         if self.cuda_graphs and all(t.is_cuda for t in inputs):
@@ -176,7 +232,7 @@ class RenderFormerRenderingPipeline:
 
     @torch.no_grad()
     def render_views(self, state: SceneState, c2w, fov, resolution: int = 512, _eager: bool = False) -> torch.Tensor:
-        eng = self.model.engine()
+        eng = self.model.engine(state.v_all.dtype)  # the operand format the scene state was built in
         if self.cuda_graphs and not _eager and getattr(state, "static", False) and c2w.is_cuda and fov.is_cuda:
             # the graph reads the persistent state in place (no copy of the 300 MB of hoisted K / V)
             return self._graph_entry(("views", id(eng), id(state), resolution, self.view_chunk) + self._sig((c2w, fov)),
@@ -230,15 +286,15 @@ class RenderFormerRenderingPipeline:
         uses texel-summed weights -- no 218 MB texel grid has to exist or be uploaded
         (`renderformer_b200.scene_io.to_pipeline_inputs(..., constant_texture=True)`).
 
-        `torch_dtype` is accepted for source compatibility and validated like the reference
-        (rendering_pipeline.py:98); the engine has a single precision policy (bf16/fp16 tensor-core
-        operands, fp32 accumulation) and always returns fp32.  Unlike the reference (:68) the
-        caller's `texture` is not modified."""
-        assert torch_dtype in (torch.bfloat16, torch.float16, torch.float32), \
-            f"Invalid precision: {torch_dtype}\nChoose from: torch.bfloat16, torch.float16, torch.float32"
+        `torch_dtype` (validated like the reference, rendering_pipeline.py:98) selects the tensor-core
+        operand format of the transformer stacks: float16 (the default, as in the reference CLIs) ->
+        fp16, bfloat16 -> bf16, float32 -> fp16 operands with a warning (`operand_dtype`); accumulation,
+        softmax, norms and the residual stream are fp32 in every mode and the result is always fp32.
+        Unlike the reference (:68) the caller's `texture` is not modified."""
+        op = operand_dtype(torch_dtype)
         if self.cuda_graphs and all(t.is_cuda for t in (triangles, texture, mask, vn, c2w, fov)):
-            return self._render_graphed((triangles, texture, mask, vn, c2w, fov), resolution)
-        state = self.encode(triangles, texture, mask, vn)
+            return self._render_graphed((triangles, texture, mask, vn, c2w, fov), resolution, op)
+        state = self.encode(triangles, texture, mask, vn, torch_dtype=op)
         return self.render_views(state, c2w, fov, resolution)
 
     def _graph_entry(self, key, inputs, fn):
@@ -273,18 +329,18 @@ class RenderFormerRenderingPipeline:
     def _sig(tensors):
         return tuple((tuple(t.shape), t.dtype) for t in tensors)
 
-    def _render_graphed(self, inputs, resolution: int) -> torch.Tensor:
-        eng = self.model.engine()
+    def _render_graphed(self, inputs, resolution: int, op: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        eng = self.model.engine(op)
 
         def run(tri, tex, mask, vn, c2w, fov):
             return self.render_views(eng.encode_scene(tri, tex, mask, vn), c2w, fov, resolution, _eager=True)
         return self._graph_entry(("render", id(eng), resolution, self.view_chunk) + self._sig(inputs), inputs, run)
 
-    def static_scene_state(self, B: int, N: int) -> SceneState:
+    def static_scene_state(self, B: int, N: int, torch_dtype: torch.dtype = torch.float16) -> SceneState:
         """The persistent SceneState of this shape (receive buffer of the NCCL broadcast on ranks that do
         not encode; one per (B, N), reused by every call so that graphs captured on it stay valid);
         `render_views` on it is replayed from a CUDA graph when `cuda_graphs` is on."""
-        eng = self.model.engine()
+        eng = self.model.engine(operand_dtype(torch_dtype))
         key = (id(eng), B, N)
         if key not in self._static_states:
             st = eng.alloc_scene_state(B, N)

@@ -97,7 +97,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None, *
     assert W.dtype == A.dtype, "operand dtypes differ"
     a.epi = epi
     if out is None and out_act is None and out16 is None:
-        ncols = N // 2 if epi == L.EPI_SWIGLU else (3 if epi == L.EPI_FINAL else N)
+        ncols = N // 2 if epi == L.EPI_SWIGLU else (3 if epi in (L.EPI_FINAL, L.EPI_FINAL_RAW) else N)
         out = torch.empty((M, ncols), dtype=out_dtype or torch.float32, device=A.device)
     ref = out if out is not None else out_act
     a.out, a.out_act = _p(out), _p(out_act)
@@ -156,6 +156,9 @@ def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0,
     a.scale = scale if scale is not None else 128 ** -0.5
     a.q_sumsq, a.k_sumsq = _p(q_sumsq), _p(k_sumsq)
     a.sumsq_ld, a.sumsq_parts, a.norm_dim, a.norm_eps = sumsq_ld, sumsq_parts, norm_dim, norm_eps
+    if not (Q.dtype == K.dtype == Vt.dtype == O.dtype) or Q.dtype not in (torch.bfloat16, torch.float16):
+        raise L.RfbError("attention operands must share one 16-bit dtype (bf16 or fp16)")
+    a.dtype = _DT[Q.dtype]
     keys = 128 if mode == 1 else Nk
     L.check(_timed("attention", 4.0 * B * H * Nq * keys * 128, lambda: lib.rfb_attention(C.byref(a), _stream()),
                    f"B={B} H={H} Nq={Nq} Nk={Nk} mode={mode}"), "rfb_attention")
@@ -169,12 +172,13 @@ def rmsnorm(x, w, out, *, rows, d, eps=1e-6, gather=None, ldx=None, ldo=None):
     return out
 
 
-def rowstat(x, out16, sumsq, *, rows, d):
-    """sumsq: [rows, parts] partial-sum layout (total in part 0, the rest cleared)."""
-    _need_cuda(x, out16, sumsq)
+def rowstat(x, out16, sumsq, *, rows, d, gather=None):
+    """sumsq: [rows, parts] partial-sum layout (total in part 0, the rest cleared).  Input row =
+    gather[r] when `gather` (int32 [rows]) is given."""
+    _need_cuda(x, out16, sumsq, gather)
     L.check(_timed("rowstat", 0.0, lambda: L.load().rfb_rowstat(
         x.data_ptr(), out16.data_ptr(), _DT[out16.dtype], out16.stride(0), sumsq.data_ptr(), sumsq.stride(0),
-        sumsq.shape[1], rows, d,
+        sumsq.shape[1], rows, d, _p(gather),
         _stream())), "rfb_rowstat")
     return out16, sumsq
 
@@ -182,9 +186,19 @@ def rowstat(x, out16, sumsq, *, rows, d):
 def qknorm_rope(x, w, out, *, rows, d, nseg, ldx, ldo, in_period=0, pos=None, freqs=None, eps=1e-6):
     _need_cuda(x, w, out)
     nf = 0 if freqs is None else freqs.numel()
-    L.check(_timed("qknorm_rope", 0.0, lambda: L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), ldo, rows, d,
+    L.check(_timed("qknorm_rope", 0.0, lambda: L.load().rfb_qknorm_rope(x.data_ptr(), ldx, in_period, w.data_ptr(), out.data_ptr(), _DT[out.dtype], ldo, rows, d,
                                      nseg, eps, _p(pos), _p(freqs), nf, _stream()),
                    f"rows={rows} d={d} nseg={nseg} period={in_period}"), "rfb_qknorm_rope")
+    return out
+
+
+def qknorm_rope_table(x, w, out, *, rows, d, nseg, ldx, ldo, cos=None, sin=None, eps=1e-6):
+    """QK-RMSNorm + RoPE from ready-made fp32 tables cos / sin [rows, >= 64] (None = norm only)."""
+    _need_cuda(x, w, out, cos, sin)
+    ldtab = 0 if cos is None else cos.stride(0)
+    L.check(_timed("qknorm_rope", 0.0, lambda: L.load().rfb_qknorm_rope_table(
+        x.data_ptr(), ldx, _p(w), out.data_ptr(), _DT[out.dtype], ldo, rows, d, nseg, eps, _p(cos), _p(sin), ldtab, _stream()),
+        f"rows={rows} d={d} nseg={nseg} table"), "rfb_qknorm_rope_table")
     return out
 
 
@@ -225,6 +239,13 @@ def ray_map_tokens(rays_d, out, *, n_views, resolution):
     _need_cuda(rays_d, out)
     L.check(_timed("ray_map_tokens", 0.0, lambda: L.load().rfb_ray_map_tokens(rays_d.data_ptr(), out.data_ptr(), n_views,
                                                                               resolution, _stream())), "rfb_ray_map_tokens")
+    return out
+
+
+def ray_map(c2w, fov_rad, out, *, n_views, resolution):
+    _need_cuda(c2w, fov_rad, out)
+    L.check(_timed("ray_map", 0.0, lambda: L.load().rfb_ray_map(c2w.data_ptr(), fov_rad.data_ptr(), out.data_ptr(), n_views,
+                                                                resolution, _stream())), "rfb_ray_map")
     return out
 
 

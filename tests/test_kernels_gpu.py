@@ -19,10 +19,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("binary,env", [
     ("selftest_gemm", {}),
+    ("selftest_gemm", {"RFB_TEST_F16": "1"}),                       # fp16 16-bit side outputs of the fused epilogues
     ("selftest_attn", {}),                       # kernel generation picked per shape
     ("selftest_attn", {"RFB_ATTN_GEN": "2"}),    # two query tiles per CTA
     ("selftest_attn", {"RFB_ATTN_GEN": "3"}),    # one query tile per CTA, Q in TMEM
-    ("selftest_attn", {"RFB_ATTN_GEN": "1", "RFB_SWIN_V1": "1"}),  # first-generation reference kernel
+    ("selftest_attn", {"RFB_TEST_F16": "1"}),                       # fp16 operands, kernel picked per shape
+    ("selftest_attn", {"RFB_TEST_F16": "1", "RFB_ATTN_GEN": "2"}),
+    ("selftest_attn", {"RFB_TEST_F16": "1", "RFB_ATTN_GEN": "3"}),
 ])
 def test_kernel_selftests(binary, env):
     exe = os.path.join(ROOT, "renderformer_b200", binary)
