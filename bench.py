@@ -534,7 +534,16 @@ def main():
             line["reference_cuda"] = ref_cuda
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down order matters: CUDA graphs that captured NCCL kernels must be gone before the communicator is
+        # (destroy_process_group with such graphs alive hung the r02c run for 24 minutes AFTER the line was printed).
+        pipe._graphs.clear()
+        pipe._static_states.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)  # skip the communicator's destructor paths altogether; every rank leaves with rc 0
 
 
 if __name__ == "__main__":

@@ -125,5 +125,17 @@ class RenderFormerConfig:
             bad.append("dropout")
         if self.dpt_features != 128 or len(self.dpt_out_channels) != 4:
             bad.append("dpt_features != 128")
+        # shape constraints of the kernels, spelled out here instead of an opaque 'rfb_gemm failed: bad argument'
+        if len(self.out_layers) != 4 or self.view_transformer_n_layers < 4:
+            bad.append("the DPT head taps exactly 4 decoder layers (dpt_out_layers)")
+        if (self.view_transformer_n_layers * self.view_transformer_latent_dim) % 256 != 0:
+            bad.append("view_transformer_n_layers * view_transformer_latent_dim must be a multiple of 256 "
+                       "(the hoisted K | V^T of all layers leave one GEMM in 256-column tiles)")
+        if 9 * (self.vertex_pe_num_freqs // 2) > 64 or 9 * (self.view_rope_dim // 2) > 64:
+            bad.append("9 * rope_dim / 2 must fit the 64 rotation pairs of a 128-wide head")
+        if self.num_register_tokens > 32:
+            bad.append("num_register_tokens <= 32")
+        if any(c % 32 for c in self.dpt_out_channels):
+            bad.append("dpt_out_channels must be multiples of 32")
         if bad:
             raise NotImplementedError("unsupported RenderFormerConfig options: " + ", ".join(bad))

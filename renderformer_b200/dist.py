@@ -155,14 +155,20 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
             ev.record(copy)
         return d, ev, mine
 
+    import os
+    import sys
+    import time
+    dbg = os.environ.get("RFB_STREAM_DEBUG") == "1" and rank == 0
     it = iter(scenes)
     first = next(it, None)
     pending = upload(first) if first is not None else None
     ring, slot, prev = [None, None, None], 0, None
     while pending is not None:
+        t_0 = time.perf_counter()
         d, ev, mine = pending
         nxt = next(it, None)
         pending = upload(nxt) if nxt is not None else None
+        t_1 = time.perf_counter()
         main.wait_event(ev)
         if sh is None:
             img = pipe.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"], resolution=resolution,
@@ -187,11 +193,16 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
             ring[slot] = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
         host = ring[slot]
         slot = (slot + 1) % 3
+        t_2 = time.perf_counter()
         host.copy_(img, non_blocking=True)
         done = torch.cuda.Event()
         done.record(main)
+        t_3 = time.perf_counter()
         if prev is not None:
             prev[1].synchronize()
+            if dbg:
+                print(f"[stream] upload-issue {1e3 * (t_1 - t_0):.2f} ms, render-issue {1e3 * (t_2 - t_1):.2f} ms, d2h-issue "
+                      f"{1e3 * (t_3 - t_2):.2f} ms, wait-prev {1e3 * (time.perf_counter() - t_3):.2f} ms", file=sys.stderr, flush=True)
             yield prev[2], prev[0]
         prev = (host, done, mine)
     if prev is not None:

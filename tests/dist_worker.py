@@ -32,6 +32,9 @@ def main():
         model.load_state_dict(init_state_dict(cfg, 7))
         pipe = RenderFormerRenderingPipeline(model)
         pipe.to(dev)
+        # one view per decoder pass everywhere: the DPT picks its convolution kernel by the number of tiles in a
+        # pass, so bit-identity needs the same view chunking in the single-GPU and in the sharded render
+        pipe.view_chunk = 1
         host = make_scene(n_tris, views, seed=3, pad_to=pad_to)
         sc = {k: v.to(dev) for k, v in host.items()}
         single = pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=res).clone()
@@ -64,10 +67,13 @@ def main():
         torch.cuda.empty_cache()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0 and flag.item() == 1:
+    good = flag.item() == 1
+    if rank == 0 and good:
         print("DIST_WORKER_OK", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1 else 1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if good else 1)  # no communicator tear-down: see bench.py
 
 
 if __name__ == "__main__":

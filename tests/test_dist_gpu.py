@@ -103,7 +103,7 @@ def test_sharded_render_equals_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_worker.py")]
     env = dict(os.environ, NCCL_DEBUG="WARN")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail
     assert "DIST_WORKER_OK" in r.stdout, tail
