@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-on-CUDA context arm (N=1 only)")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from Python")
-    ap.add_argument("--view-chunk", type=int, default=4, help="views per decoder pass")
+    ap.add_argument("--view-chunk", type=int, default=8, help="views per decoder pass (capped by the views a rank renders)")
     ap.add_argument("--view-streams", type=int, default=1, help="CUDA streams the view chunks are spread over")
     ap.add_argument("--ref-cuda-worker", default="", help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -342,10 +342,11 @@ def main():
     model.engine(torch.bfloat16)
     R, N = args.resolution, args.tris
     V = job_views(args, world)
-    pipe.view_chunk = max(1, args.view_chunk)
     pipe.view_streams = args.view_streams
     mine = view_slice(V, world, rank)
     Vl = mine.stop - mine.start
+    # same chunking on every rank (and in the single-GPU check render): the per-rank view count caps it
+    pipe.view_chunk = max(1, min(args.view_chunk, -(-V // world)))
 
     scene = make_scene(N, V, seed=0)
     host = {k: v.pin_memory() for k, v in scene.items()}

@@ -27,8 +27,6 @@ int launch_attention_swin(const CUtensorMap& tmQ, const CUtensorMap& tmK, const 
                           const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_attn_args* a, int k_batched,
                       int v_batched, cudaStream_t stream);
-int launch_attention4(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_attn_args* a, int k_batched,
-                      int v_batched, cudaStream_t stream);
 int launch_attention2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const rfb_attn_args* a, int k_batched, int v_batched, cudaStream_t stream);
 
@@ -68,23 +66,22 @@ extern "C" int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream_) {
   }
 
   if (a->mode == 0) {
-    static int forced = -1;  // RFB_ATTN_GEN = 2 | 3 | 4 forces one dense kernel generation (A/B runs)
+    static int forced = -1;  // RFB_ATTN_GEN = 2 | 3 forces one dense kernel generation (A/B runs)
     if (forced < 0) {
       const char* e = getenv("RFB_ATTN_GEN");
-      forced = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 0;
+      forced = (e && e[0] >= '2' && e[0] <= '3') ? e[0] - '0' : 0;
     }
     int gen = forced;
     if (gen == 0) {
-      // What differs first is how evenly the grids fill the SMs (one CTA per SM): two-tile CTAs (gen 2) vs
-      // one-tile CTAs (gen 4: two softmax threads per row; gen 3 is its one-thread-per-row predecessor).
+      // Both kernels sustain the same rate per tile; what differs is how evenly their grids fill
+      // the SMs (one CTA per SM): two-tile CTAs (gen 2) vs one-tile CTAs (gen 3).
       const int sms = num_sms();
       const long long n2 = (long long)((a->Nq + 255) / 256) * a->H * a->B;
       const long long n3 = (long long)((a->Nq + 127) / 128) * a->H * a->B;
       const double e2 = (double)n2 / (double)(((n2 + sms - 1) / sms) * sms);
       const double e3 = (double)n3 / (double)(((n3 + sms - 1) / sms) * sms);
-      gen = (e3 > e2 + 0.02) ? 4 : 2;
+      gen = (e3 > e2 + 0.02) ? 3 : 2;
     }
-    if (gen == 4) return launch_attention4(tmK, tmV, a, k_batched, v_batched, stream);
     if (gen == 3) return launch_attention3(tmK, tmV, a, k_batched, v_batched, stream);
     return launch_attention2(tmQ, tmK, tmV, a, k_batched, v_batched, stream);
   }

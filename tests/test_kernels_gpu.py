@@ -23,11 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("selftest_attn", {}),                       # kernel generation picked per shape
     ("selftest_attn", {"RFB_ATTN_GEN": "2"}),    # two query tiles per CTA
     ("selftest_attn", {"RFB_ATTN_GEN": "3"}),    # one query tile per CTA, Q in TMEM
-    ("selftest_attn", {"RFB_ATTN_GEN": "4"}),    # one query tile per CTA, two softmax threads per row
     ("selftest_attn", {"RFB_TEST_F16": "1"}),                       # fp16 operands, kernel picked per shape
     ("selftest_attn", {"RFB_TEST_F16": "1", "RFB_ATTN_GEN": "2"}),
     ("selftest_attn", {"RFB_TEST_F16": "1", "RFB_ATTN_GEN": "3"}),
-    ("selftest_attn", {"RFB_TEST_F16": "1", "RFB_ATTN_GEN": "4"}),
 ])
 def test_kernel_selftests(binary, env):
     exe = os.path.join(ROOT, "renderformer_b200", binary)
