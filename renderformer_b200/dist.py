@@ -136,24 +136,20 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
     world, rank = _world()
     main = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(dev)
-    from .model import operand_dtype
+    from .model import UploadRing, operand_dtype
     eng = pipe.model.engine(operand_dtype(torch_dtype))
     sh = row_shard()
+    up = UploadRing(dev, copy)
 
     def upload(sc):
         V = sc["c2w"].shape[1]
         mine = view_slice(V, world, rank)
         N = sc["triangles"].shape[1]
         t0, t1 = eng.own_triangles(N, sh) if sh is not None else (0, N)
-        with torch.cuda.stream(copy):
-            d = {"c2w": sc["c2w"][:, mine].contiguous().to(dev, non_blocking=True),
-                 "fov": sc["fov"][:, mine].contiguous().to(dev, non_blocking=True)}
-            for k in ("triangles", "mask", "vn"):
-                d[k] = sc[k].to(dev, non_blocking=True)
-            d["texture"] = sc["texture"][:, t0:t1].to(dev, non_blocking=True)  # contiguous for one scene per batch
-            ev = torch.cuda.Event()
-            ev.record(copy)
-        return d, ev, mine
+        d, ev, slot = up.put({"c2w": sc["c2w"][:, mine], "fov": sc["fov"][:, mine], "triangles": sc["triangles"],
+                              "mask": sc["mask"], "vn": sc["vn"],
+                              "texture": sc["texture"][:, t0:t1]})  # only this rank's rows of the texture
+        return d, ev, mine, slot
 
     import os
     import sys
@@ -162,10 +158,10 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
     it = iter(scenes)
     first = next(it, None)
     pending = upload(first) if first is not None else None
-    ring, slot, prev = [None, None, None], 0, None
+    ring, rslot, prev = [None, None, None], 0, None
     while pending is not None:
         t_0 = time.perf_counter()
-        d, ev, mine = pending
+        d, ev, mine, slot = pending
         nxt = next(it, None)
         pending = upload(nxt) if nxt is not None else None
         t_1 = time.perf_counter()
@@ -185,14 +181,13 @@ def render_stream_sharded(pipe, scenes, resolution: int = 512, ldr: Optional[str
                 img = pipe._graph_entry(key, inputs, run)
             else:
                 img = run(*inputs)
-        for t in d.values():
-            t.record_stream(main)
+        up.release(slot, main)
         if ldr is not None:
             img = pipe.hdr_to_ldr(img, ldr)
-        if ring[slot] is None or ring[slot].shape != img.shape or ring[slot].dtype != img.dtype:
-            ring[slot] = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
-        host = ring[slot]
-        slot = (slot + 1) % 3
+        if ring[rslot] is None or ring[rslot].shape != img.shape or ring[rslot].dtype != img.dtype:
+            ring[rslot] = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+        host = ring[rslot]
+        rslot = (rslot + 1) % 3
         t_2 = time.perf_counter()
         host.copy_(img, non_blocking=True)
         done = torch.cuda.Event()

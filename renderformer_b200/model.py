@@ -157,6 +157,47 @@ class RenderFormer(nn.Module):
         return torch.log10(hdr + 1.0).permute(0, 1, 4, 2, 3)
 
 
+class UploadRing:
+    """Persistent device staging buffers for host -> device uploads on a copy stream.
+
+    Fresh `tensor.to(device)` allocations per scene looked free until the caching allocator had to fall back
+    to cudaMalloc for a 100-200 MB block while the previous blocks were still pinned down by
+    `record_stream`: that call waits for the device and stalled the host for ~25 ms every other scene
+    (r02f).  Here slot i % depth is overwritten only after the consumer of its previous content has been
+    enqueued (`release`), and nothing is allocated in steady state."""
+
+    def __init__(self, device, copy_stream, depth: int = 2):
+        self.dev, self.copy, self.depth = device, copy_stream, depth
+        self.slots = [dict() for _ in range(depth)]
+        self.free = [None] * depth
+        self.n = 0
+
+    def put(self, host_tensors: dict):
+        """-> (device tensors, event that fires when they are complete, slot)."""
+        slot = self.n % self.depth
+        self.n += 1
+        bufs = self.slots[slot]
+        for k, t in host_tensors.items():
+            b = bufs.get(k)
+            if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                bufs[k] = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+        if self.free[slot] is not None:
+            self.copy.wait_event(self.free[slot])
+        else:  # first use: the buffers were allocated on the current stream
+            self.copy.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.copy):
+            for k, t in host_tensors.items():
+                bufs[k].copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        return {k: bufs[k] for k in host_tensors}, ev, slot
+
+    def release(self, slot: int, consumer_stream) -> None:
+        ev = torch.cuda.Event()
+        ev.record(consumer_stream)
+        self.free[slot] = ev
+
+
 _warned_fp32 = [False]
 
 
@@ -378,27 +419,23 @@ class RenderFormerRenderingPipeline:
         keys = ("triangles", "texture", "mask", "vn", "c2w", "fov")
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
+        up = UploadRing(dev, copy)
 
         def upload(sc):
-            with torch.cuda.stream(copy):
-                d = {k: sc[k].to(dev, non_blocking=True) for k in keys}
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            return d, ev
+            return up.put({k: sc[k] for k in keys})
 
         it = iter(scenes)
         first = next(it, None)
         pending = upload(first) if first is not None else None
         ring, slot, prev = [None, None, None], 0, None
         while pending is not None:
-            d, ev = pending
+            d, ev, uslot = pending
             nxt = next(it, None)
             pending = upload(nxt) if nxt is not None else None  # overlaps with this scene's kernels
             main.wait_event(ev)
             img = self.render(d["triangles"], d["texture"], d["mask"], d["vn"], d["c2w"], d["fov"],
                               resolution=resolution, torch_dtype=torch_dtype)
-            for t in d.values():
-                t.record_stream(main)  # allocated on the copy stream, consumed on the main stream
+            up.release(uslot, main)  # the staging slot may be overwritten once this render has consumed it
             if ldr is not None:
                 img = self.hdr_to_ldr(img, ldr)
             if ring[slot] is None or ring[slot].shape != img.shape or ring[slot].dtype != img.dtype:
