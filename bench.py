@@ -476,11 +476,12 @@ def main():
             traffic, traffic_src = None, None
             for name in ("r02_gemm_traffic.json", "r01e_gemm_traffic.json"):
                 tpath = os.path.join(ROOT, "profiles", name)
-                if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, pipe.view_chunk) == (4096, 512, 4):
+                want_chunk = 8 if name.startswith("r02") else 4
+                if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, pipe.view_chunk) == (4096, 512, want_chunk):
                     with open(tpath) as f:
                         tj = json.load(f)
                     traffic = tj["dram_bytes_per_launch"]
-                    traffic_src = f"profiles/{name} (ncu dram__bytes_read+write, avg over the GEMM launches of one scene + 4-view chunk)"
+                    traffic_src = f"profiles/{name} (ncu dram__bytes_read+write, average over consecutive GEMM / conv launches of this job)"
                     break
             roofline = {
                 "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",

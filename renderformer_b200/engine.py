@@ -58,6 +58,11 @@ class SceneState:
     def tensors(self):
         return [self.seq, self.tri, self.mask_u8, self.mask_bits, self.k_all, self.v_all]
 
+    @property
+    def complete(self) -> bool:
+        """False when `seq` holds only this rank's rows (row-sharded encode without `gather_seq`)."""
+        return self.seq is not None and self.seq.shape[1] == self.Ntp
+
 
 @dataclass
 class RowShard:
@@ -281,16 +286,18 @@ class Engine:
     @torch.no_grad()
     def encode_scene(self, triangles, texture, mask, vn, texture_is_log: bool = False,
                      shard: Optional[RowShard] = None, texture_own_rows: bool = False,
-                     taps: Optional[dict] = None) -> SceneState:
+                     taps: Optional[dict] = None, gather_seq: bool = False) -> SceneState:
         """View-independent stage.  With `shard` (multi-GPU) every rank passes the same scene and runs
         the row-sharded schedule `_encode_scene_sharded`; every rank returns the complete SceneState.
         `texture_own_rows`: `texture` holds only the triangles of this rank's rows
-        (`own_triangles(N, shard)`), so a rank never has to upload the other ranks' texels."""
+        (`own_triangles(N, shard)`), so a rank never has to upload the other ranks' texels.
+        `gather_seq`: also all-gather the fp32 token sequence `SceneState.seq` (nothing downstream needs it: the
+        view stage reads the hoisted K / V; without it `seq` holds this rank's own rows only)."""
         cfg, w, dev = self.cfg, self.w, self.device
         if shard is not None and shard.world > 1:
             B = triangles.shape[0]
             sts = [self._encode_scene_sharded(triangles[b:b + 1], texture[b:b + 1], mask[b:b + 1], vn[b:b + 1],
-                                              texture_is_log, shard, texture_own_rows) for b in range(B)]
+                                              texture_is_log, shard, texture_own_rows, gather_seq) for b in range(B)]
             if B == 1:
                 return sts[0]
             cat = [torch.cat(ts, dim=0) for ts in zip(*(st.tensors() for st in sts))]
@@ -420,7 +427,7 @@ class Engine:
         return min(max(r0 - nreg, 0), N), min(max(r1 - nreg, 0), N)
 
     def _encode_scene_sharded(self, triangles, texture, mask, vn, texture_is_log, sh: RowShard,
-                              texture_own_rows: bool = False) -> SceneState:
+                              texture_own_rows: bool = False, gather_seq: bool = False) -> SceneState:
         """One scene, token rows split over the ranks of `sh` (see RowShard).  Per layer and rank:
         [q|k|v] projection of ALL rows from the gathered 16-bit stream (K and V are needed for every
         key; 26 GFLOP, replicated), QK-norm + RoPE, attention of the OWN query rows against all keys,
@@ -508,7 +515,8 @@ class Engine:
         # hoisted decoder K / V of ALL layers from the gathered stream, replicated on every rank (0.2 TFLOP:
         # cheaper than moving the 300 MB result over NVLink)
         k_all, v_all = self.hoist_kv(xb_all, xsq_all, 1, Ntp)
-        # the fp32 token sequence itself (API completeness / tests): one more gather
+        if not gather_seq:  # the fp32 token sequence is not needed downstream: keep the own rows, skip the collective
+            return SceneState(1, N, Nt, Ntp, x[:rows].view(1, rows, d), tri, mask_u8, bits, k_all, v_all, dv)
         seq = self._e((sh.world * S, d), f32)
         if rows > 0:
             seq[r0:r1].copy_(x[:rows])

@@ -76,8 +76,8 @@ def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world):
             step[0] += 1
 
         sh = RowShard(rank, world, fake_all_gather)
-        st = eng.encode_scene(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], shard=sh)
-        assert step[0] == cfg.num_layers + 1
+        st = eng.encode_scene(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], shard=sh, gather_seq=True)
+        assert step[0] == cfg.num_layers + 1 and st.complete
         for a, b, name in zip(st.tensors(), ref.tensors(), ("seq", "tri", "mask", "bits", "k_all", "v_all")):
             assert a.shape == b.shape, name
             assert torch.equal(a, b), f"rank {rank}: SceneState.{name} differs from the single-GPU schedule"
@@ -86,7 +86,7 @@ def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world):
         step[0] = 0
         st2 = eng.encode_scene(sc["triangles"], sc["texture"][:, t0:t1].contiguous(), sc["mask"], sc["vn"], shard=sh,
                                texture_own_rows=True)
-        assert torch.equal(st2.k_all, ref.k_all) and torch.equal(st2.v_all, ref.v_all)
+        assert torch.equal(st2.k_all, ref.k_all) and torch.equal(st2.v_all, ref.v_all) and not (world > 1 and st2.complete)
 
 
 def _free_port():
@@ -97,8 +97,7 @@ def _free_port():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_render_equals_single_gpu():
-    n = min(torch.cuda.device_count(), 8)
-    n = 8 if n >= 8 else (4 if n >= 4 else 2)
+    n = 2  # two ranks exercise every code path; bench.py re-checks bit-identity at whatever N it runs on
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_worker.py")]
