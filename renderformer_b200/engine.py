@@ -562,14 +562,15 @@ class Engine:
     def render_views(self, st: SceneState, b: int, c2w: Optional[torch.Tensor], fov_deg: Optional[torch.Tensor],
                      resolution: int, taps: Optional[dict] = None, rays_d: Optional[torch.Tensor] = None,
                      tri_cam: Optional[torch.Tensor] = None, pos_cam: Optional[torch.Tensor] = None,
-                     raw_log: bool = False) -> torch.Tensor:
+                     raw_log: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Render V views of scene `b` -> HDR fp32 [V,R,R,3].  Either cameras (c2w [V,4,4], fov_deg [V] or
         [V,1]; rays and camera-space triangles are derived on the device) or, for the model-level entry
         (models/renderformer.py:171-206), an explicit camera-space ray map `rays_d` [V,R,R,3] together
         with the camera-space triangles `tri_cam` [V,N,9] -- or the ready RoPE positions `pos_cam`
         [V,Nt,9] (register centroids included) as ViewTransformer.forward receives them
         (models/view_transformer.py:88).  `raw_log`: return the head's pre-ELU output [V,R,R,3] instead
-        (DPTHead.forward, layers/dpt.py:242-273)."""
+        (DPTHead.forward, layers/dpt.py:242-273).  `out`: contiguous fp32 [V,R,R,3] buffer the last kernel
+        writes the image into (a slice of the caller's result tensor: no concatenation afterwards)."""
         cfg, dev = self.cfg, self.device
         explicit = rays_d is not None
         if explicit and tri_cam is None and pos_cam is None:
@@ -600,7 +601,7 @@ class Engine:
                                 n_reg=cfg.num_register_tokens, rows_out=Ntp, n_views=V)
             x = self.ray_tokens(V, R, fov=fov)
         feats = self.decoder_layers(st, b, x, pos, V, Hp, Wp, taps)
-        return self._dpt(feats, V, Hp, Wp, raw_out=raw_log)
+        return self._dpt(feats, V, Hp, Wp, raw_out=raw_log, out=out)
 
     def ray_tokens(self, V: int, R: int, fov=None, rays=None):
         """Ray-bundle patch tokens x fp32 [V*(R/8)^2, dv]: pinhole rays (utils/ray_generator.py:13-50) or an
@@ -744,7 +745,7 @@ class Engine:
         o = ops.gemm(o, self.w[name + "out.w"], bias=self.w[name + "out.b"], out=self._e((B * H * W, F_), hf))
         return ops.upsample_bilinear(o, self._e((B * Ho * Wo, F_), hf), B=B, Hi=H, Wi=W, Ho=Ho, Wo=Wo, C_=F_)
 
-    def _dpt(self, feats, V, Hp, Wp, raw_out: bool = False):
+    def _dpt(self, feats, V, Hp, Wp, raw_out: bool = False, out: Optional[torch.Tensor] = None):
         """DPTHead.forward (layers/dpt.py:242-273) on four fp16 feature maps [V*Hp*Wp, dv] -> HDR image fp32
         [V, 8Hp, 8Wp, 3] (the head's ELU and the pipeline's 10^x - 1 are the last conv's epilogue), or with
         `raw_out` the head's own output before the ELU."""
@@ -777,7 +778,9 @@ class Engine:
         p1 = self._fusion(1, V, *dims[0], Ho, Wo, p2, lraw[0], lact[0])
         # head (layers/dpt.py:266-271); F.interpolate to (8*Hp, 8*Wp) is the identity here (E2)
         o1 = self._conv(p1, "dpt.oc1", V, Ho, Wo, F_, bias=w["dpt.oc1.b"], out=self._e((V * Ho * Wo, F_ // 2), hf))
-        img = self._e((V, Ho, Wo, 3), torch.float32)
+        if out is not None and (tuple(out.shape) != (V, Ho, Wo, 3) or out.dtype != torch.float32 or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous fp32 [V, H, W, 3] tensor")
+        img = out if out is not None else self._e((V, Ho, Wo, 3), torch.float32)
         self._conv(o1, "dpt.oc2", V, Ho, Wo, F_ // 2, bias=w["dpt.oc2.b"], epi=L.EPI_FINAL_RAW if raw_out else L.EPI_FINAL,
                    w2=w["dpt.oc3.w"], b2=w["dpt.oc3.b"], out=img, ldo=3)
         return img

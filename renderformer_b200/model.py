@@ -282,39 +282,32 @@ class RenderFormerRenderingPipeline:
         if V == 0:  # a rank whose view slice is empty (fewer views than ranks)
             return torch.empty((B, 0, resolution, resolution, 3), dtype=torch.float32, device=self.device)
         jobs = [(b, v0) for b in range(B) for v0 in range(0, V, self.view_chunk)]
+        # every decoder pass writes its images straight into its slice of the result (no torch.cat afterwards)
+        result = torch.empty((B, V, resolution, resolution, 3), dtype=torch.float32, device=self.device)
         n_str = min(self.view_streams, len(jobs))
         if n_str <= 1:
-            res = [eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
-                                    resolution) for b, v0 in jobs]
-        else:
-            dev = self.device
-            while len(self._side_streams) < n_str:
-                self._side_streams.append(torch.cuda.Stream(dev))
-            cur = torch.cuda.current_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            res, joins = [], []
-            for i, (b, v0) in enumerate(jobs):
-                side = self._side_streams[i % n_str]
-                if i < n_str:
-                    side.wait_event(fork)
-                with torch.cuda.stream(side):
-                    img = eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk],
-                                           resolution)
-                img.record_stream(cur)
-                res.append(img)
-            for side in self._side_streams[:n_str]:
-                ev = torch.cuda.Event()
-                ev.record(side)
-                joins.append(ev)
-            for ev in joins:
-                cur.wait_event(ev)
-        out = []
-        per_b = len(jobs) // B
-        for b in range(B):
-            chunks = res[b * per_b:(b + 1) * per_b]
-            out.append(torch.cat(chunks, dim=0) if len(chunks) > 1 else chunks[0])
-        return torch.stack(out, dim=0)
+            for b, v0 in jobs:
+                eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk], resolution,
+                                 out=result[b, v0:v0 + self.view_chunk])
+            return result
+        dev = self.device
+        while len(self._side_streams) < n_str:
+            self._side_streams.append(torch.cuda.Stream(dev))
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for i, (b, v0) in enumerate(jobs):
+            side = self._side_streams[i % n_str]
+            if i < n_str:
+                side.wait_event(fork)
+            with torch.cuda.stream(side):
+                eng.render_views(state, b, c2w[b, v0:v0 + self.view_chunk], fov[b, v0:v0 + self.view_chunk], resolution,
+                                 out=result[b, v0:v0 + self.view_chunk])
+        for side in self._side_streams[:n_str]:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            cur.wait_event(ev)
+        return result
 
     @torch.no_grad()
     def render(self, triangles, texture, mask, vn, c2w, fov, resolution: int = 512,
