@@ -64,83 +64,40 @@ __device__ __forceinline__ void h8_to_f(const uint4& u, float (&f)[8]) {
 }
 
 // bilinear, align_corners=True: src = dst * (in-1)/(out-1)   (F.interpolate, layers/dpt.py:154-155)
-// One thread produces a 2 x 2 block of output pixels for 8 channels: the four outputs share their source
-// pixels (a 3 x 3 neighbourhood at most for scale factors >= 1), so a thread issues <= 9 independent 16-byte
-// loads and 4 stores instead of 4 loads per store -- 2.25 instead of 4 L1/L2 requests per output vector and four
-// times the stores in flight per thread (the kernel is bound by the 2 B/element output stream to HBM).
 __global__ void upsample_bilinear_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int Hi,
                                          int Wi, int Ho, int Wo, int C8) {
-  const int Hq = (Ho + 1) >> 1, Wq = (Wo + 1) >> 1;
-  const long long total = (long long)B * Hq * Wq * C8;
+  const long long total = (long long)B * Ho * Wo * C8;
   const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const int c = t % C8;
     long long r = t / C8;
-    const int xq = r % Wq;
-    r /= Wq;
-    const int yq = r % Hq;
-    const int b = r / Hq;
-    int ys[2][2], xs[2][2];
-    float wy[2], wx[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float fy = min(2 * yq + i, Ho - 1) * sy, fx = min(2 * xq + i, Wo - 1) * sx;
-      const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
-      ys[i][0] = y0, ys[i][1] = min(y0 + 1, Hi - 1), wy[i] = fy - y0;
-      xs[i][0] = x0, xs[i][1] = min(x0 + 1, Wi - 1), wx[i] = fx - x0;
-    }
+    const int xo = r % Wo;
+    r /= Wo;
+    const int yo = r % Ho;
+    const int b = r / Ho;
+    const float fy = yo * sy, fx = xo * sx;
+    int y0 = (int)fy, x0 = (int)fx;
+    y0 = min(y0, Hi - 1), x0 = min(x0, Wi - 1);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float wy = fy - y0, wx = fx - x0;
     const uint4* base = in + (long long)b * Hi * Wi * C8 + c;
-    // distinct source rows / columns of the block: ys[0][0] <= ys[0][1] <= ... (monotone), same for x
-    uint4 v[2][2][2][2];  // [out row i][row tap][out col j][col tap]
+    float a[8], bb[8], cc[8], d[8];
+    h8_to_f(__ldg(base + ((long long)y0 * Wi + x0) * C8), a);
+    h8_to_f(__ldg(base + ((long long)y0 * Wi + x1) * C8), bb);
+    h8_to_f(__ldg(base + ((long long)y1 * Wi + x0) * C8), cc);
+    h8_to_f(__ldg(base + ((long long)y1 * Wi + x1) * C8), d);
+    float o[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int tx = 0; tx < 2; ++tx) {
-            // reuse a register that already holds this source pixel (compile-time unrolled comparisons)
-            bool have = false;
-#pragma unroll
-            for (int pi = 0; pi <= i; ++pi)
-#pragma unroll
-              for (int pty = 0; pty < 2; ++pty)
-#pragma unroll
-                for (int pj = 0; pj < 2; ++pj)
-#pragma unroll
-                  for (int ptx = 0; ptx < 2; ++ptx) {
-                    const bool earlier = (((pi * 2 + pty) * 2 + pj) * 2 + ptx) < (((i * 2 + ty) * 2 + j) * 2 + tx);
-                    if (!have && earlier && ys[pi][pty] == ys[i][ty] && xs[pj][ptx] == xs[j][tx]) {
-                      v[i][ty][j][tx] = v[pi][pty][pj][ptx];
-                      have = true;
-                    }
-                  }
-            if (!have) v[i][ty][j][tx] = __ldg(base + ((long long)ys[i][ty] * Wi + xs[j][tx]) * C8);
-          }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int yo = 2 * yq + i;
-      if (yo >= Ho) continue;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int xo = 2 * xq + j;
-        if (xo >= Wo) continue;
-        float a[8], bb[8], cc[8], d[8], o[8];
-        h8_to_f(v[i][0][j][0], a), h8_to_f(v[i][0][j][1], bb), h8_to_f(v[i][1][j][0], cc), h8_to_f(v[i][1][j][1], d);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float top = a[k] + (bb[k] - a[k]) * wx[j];
-          const float bot = cc[k] + (d[k] - cc[k]) * wx[j];
-          o[k] = top + (bot - top) * wy[i];
-        }
-        uint4 u;
-        u.x = pack_f16(o[0], o[1]), u.y = pack_f16(o[2], o[3]), u.z = pack_f16(o[4], o[5]), u.w = pack_f16(o[6], o[7]);
-        out[(((long long)b * Ho + yo) * Wo + xo) * C8 + c] = u;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float top = a[i] + (bb[i] - a[i]) * wx;
+      const float bot = cc[i] + (d[i] - cc[i]) * wx;
+      o[i] = top + (bot - top) * wy;
     }
+    uint4 u;
+    u.x = pack_f16(o[0], o[1]), u.y = pack_f16(o[2], o[3]), u.z = pack_f16(o[4], o[5]), u.w = pack_f16(o[6], o[7]);
+    out[t] = u;
   }
 }
 
@@ -216,7 +173,7 @@ extern "C" int rfb_im2col_s2(const void* in, void* out, int B, int H, int W, int
 extern "C" int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                      rfb_stream_t stream) {
   if (!in || !out || C % 8) return RFB_ERR_ARG;
-  const long long total = (long long)B * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 8);  // one thread per 2 x 2 output block
+  const long long total = (long long)B * Ho * Wo * (C / 8);
   upsample_bilinear_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B,
                                                                               Hi, Wi, Ho, Wo, C / 8);
   g_launch_count++;
