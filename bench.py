@@ -414,6 +414,39 @@ def main():
             pipe.cuda_graphs = graphs
         dist.barrier()
 
+    # ---- where the step goes: scene stage / view stage / image gather, each replayed from its own CUDA graph
+    # (outside the timed region; max over ranks per stage, so the parts can add up to a little more than ms_step)
+    stages = None
+    try:
+        from renderformer_b200.dist import gather_images, row_shard
+        sh = row_shard()
+        cl, fl = d_in["c2w"][:, mine].contiguous(), d_in["fov"][:, mine].contiguous()
+        sizes = [view_slice(V, world, r).stop - view_slice(V, world, r).start for r in range(world)]
+
+        def staged(ev):
+            ev[0].record()
+            st = pipe.encode(d_in["triangles"], d_in["texture"], d_in["mask"], d_in["vn"], shard=sh, torch_dtype=torch.bfloat16)
+            ev[1].record()
+            img = pipe.render_views(st, cl, fl, R)
+            ev[2].record()
+            if world > 1:
+                gather_images(img[0], dst=0, sizes=sizes)
+            ev[3].record()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(4)]
+        for i in range(2):
+            staged(evs[i])
+        barrier()
+        for i in range(2, 4):
+            staged(evs[i])
+        barrier()
+        t = torch.tensor([[e[k].elapsed_time(e[k + 1]) for k in range(3)] for e in evs[2:]], device=dev).mean(dim=0)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages = {"scene_stage_ms": t[0].item(), "view_stage_ms": t[1].item(), "image_gather_ms": t[2].item(),
+                  "note": "separate CUDA-graph replays per stage, max over ranks"}
+    except Exception as e:  # noqa: BLE001  (diagnostic only)
+        stages = {"unavailable": repr(e)[:200]}
+
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
@@ -530,6 +563,7 @@ def main():
                 "scene_tflop": scene_flops(cfg, N) / 1e12, "view_tflop": view_flops(cfg, N, R) / 1e12,
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "stages": stages,
             "sharded_equals_single": sharded_equals_single,
         }
         if ref_cuda is not None:

@@ -172,22 +172,40 @@ class UploadRing:
         self.free = [None] * depth
         self.n = 0
 
-    def put(self, host_tensors: dict):
-        """-> (device tensors, event that fires when they are complete, slot)."""
+    PER_TRIANGLE = ("triangles", "texture", "mask", "vn")
+
+    def put(self, host_tensors: dict, pad_to: Optional[int] = None):
+        """-> (device tensors, event that fires when they are complete, slot).  With `pad_to` the per-triangle
+        tensors land in the first N rows of buffers with `pad_to` rows (batch_infer.py:37-47 pads every scene of
+        a folder to one length): the mask tail is cleared, the other tails keep whatever an earlier scene left
+        there -- masked triangles never reach a valid token."""
         slot = self.n % self.depth
         self.n += 1
         bufs = self.slots[slot]
+        fresh = False
         for k, t in host_tensors.items():
+            shape = tuple(t.shape)
+            if pad_to is not None and k in self.PER_TRIANGLE:
+                if t.shape[1] > pad_to:
+                    raise ValueError(f"scene has {t.shape[1]} triangles, pad_to is {pad_to}")
+                shape = (t.shape[0], pad_to) + tuple(t.shape[2:])
             b = bufs.get(k)
-            if b is None or b.shape != t.shape or b.dtype != t.dtype:
-                bufs[k] = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+            if b is None or tuple(b.shape) != shape or b.dtype != t.dtype:
+                bufs[k] = torch.zeros(shape, dtype=t.dtype, device=self.dev)
+                fresh = True
         if self.free[slot] is not None:
             self.copy.wait_event(self.free[slot])
-        else:  # first use: the buffers were allocated on the current stream
+        if fresh or self.free[slot] is None:  # buffers were allocated / zeroed on the current stream
             self.copy.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.copy):
             for k, t in host_tensors.items():
-                bufs[k].copy_(t, non_blocking=True)
+                if pad_to is not None and k in self.PER_TRIANGLE:
+                    n = t.shape[1]
+                    bufs[k][:, :n].copy_(t, non_blocking=True)
+                    if k == "mask" and n < pad_to:
+                        bufs[k][:, n:] = False
+                else:
+                    bufs[k].copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy)
         return {k: bufs[k] for k in host_tensors}, ev, slot
@@ -227,14 +245,17 @@ class RenderFormerRenderingPipeline:
         # Opt-in CUDA-graph replay of `render` (pipeline.cuda_graphs = True): the ~220 kernel launches
         # of a call are captured once per input signature and replayed, which removes the host launch
         # cost (dominant for small scenes / low resolutions) and shrinks the gaps between kernels.
-        # The returned tensor is then the graph's static output: valid until the next call with the
-        # same signature.  Each cached graph pins its activations (a few GB for Large at 512^2).
+        # Each cached graph pins its activations (a few GB for Large at 512^2).
         # Independent view chunks can run on several CUDA streams: kernels of different chunks then fill
         # each other's partial last waves and ramp-up / drain bubbles (every kernel here occupies a whole
         # SM per CTA).  1 = sequential chunks.
         self.view_streams = 1
         self._side_streams = []
         self.cuda_graphs = False
+        # `render` hands out a copy of the graph's static output (0.07 ms for 32 frames) so that results of
+        # consecutive calls stay valid; set True to receive the static tensor itself (overwritten by the next
+        # call with the same signature)
+        self.graph_static_outputs = False
         self.max_cached_graphs = 4
         self._graphs = {}
         self._static_states = {}
@@ -327,7 +348,8 @@ class RenderFormerRenderingPipeline:
         Unlike the reference (:68) the caller's `texture` is not modified."""
         op = operand_dtype(torch_dtype)
         if self.cuda_graphs and all(t.is_cuda for t in (triangles, texture, mask, vn, c2w, fov)):
-            return self._render_graphed((triangles, texture, mask, vn, c2w, fov), resolution, op)
+            out = self._render_graphed((triangles, texture, mask, vn, c2w, fov), resolution, op)
+            return out if self.graph_static_outputs else out.clone()
         state = self.encode(triangles, texture, mask, vn, torch_dtype=op)
         return self.render_views(state, c2w, fov, resolution)
 
@@ -394,7 +416,7 @@ class RenderFormerRenderingPipeline:
 
     @torch.no_grad()
     def render_stream(self, scenes, resolution: int = 512, torch_dtype: torch.dtype = torch.float16,
-                      ldr: Optional[str] = None):
+                      ldr: Optional[str] = None, pad_to: Optional[int] = None):
         """Render a sequence of scenes given as HOST tensors (the batch_infer.py use case,
         batch_infer.py:103-143): generator over dicts with the keys of `render` ('triangles', 'texture',
         'mask', 'vn', 'c2w', 'fov'), yielding one pinned-host fp32 HDR tensor [B,V,H,W,3] per scene,
@@ -405,7 +427,11 @@ class RenderFormerRenderingPipeline:
         i+1; pass pinned tensors for truly asynchronous copies.  A yielded buffer belongs to a ring
         of three and is overwritten two scenes later -- copy it if it must live longer.
         `ldr='none' | 'pbr_neutral'` tone-maps and quantises on the device and yields uint8 images
-        (a quarter of the download)."""
+        (a quarter of the download).
+        `pad_to=N`: scenes with different triangle counts are padded ON THE DEVICE to N triangles (mask False
+        behind the real ones, what batch_infer.py:37-47 does on the host with `--padding_length`), so every
+        scene has the same input signature and, with `cuda_graphs`, ONE captured graph replays for all of
+        them; the images equal those of the unpadded scenes."""
         dev = self.device
         if dev.type != "cuda":
             raise L.RfbError("render_stream needs a CUDA device (there is no CPU fallback)")
@@ -415,7 +441,7 @@ class RenderFormerRenderingPipeline:
         up = UploadRing(dev, copy)
 
         def upload(sc):
-            return up.put({k: sc[k] for k in keys})
+            return up.put({k: sc[k] for k in keys}, pad_to=pad_to)
 
         it = iter(scenes)
         first = next(it, None)

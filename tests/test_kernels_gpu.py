@@ -56,6 +56,7 @@ def _check(pipe, sd, cfg, sc, res, tag):
     rel, psnr = hdr_rel_err(img, ref), log_psnr(img, ref)
     print(f"{tag}: hdr rel {rel:.3e} log-PSNR {psnr:.1f} dB")
     assert rel <= REL_TOL and psnr >= PSNR_MIN, tag
+    return ref
 
 
 @pytest.mark.parametrize("cfg_name,n_tris,pad_to,views,res", [
@@ -111,6 +112,28 @@ def test_render_stream_matches_blocking_calls():
     assert list(pipe.render_stream(iter([]), resolution=64)) == []
 
 
+def test_render_stream_fixed_length_padding_reuses_one_graph():
+    """batch_infer.py:37-47 (`--padding_length`): scenes of different triangle counts padded to one length on the
+    device -> one input signature -> ONE CUDA graph replayed for every scene; images equal the unpadded renders."""
+    cfg = RenderFormerConfig.named("tiny_swin")
+    pipe, _ = _pipe(cfg, 8)
+    counts = (61, 128, 17, 100)
+    scenes = [make_scene(n, 2, seed=40 + i) for i, n in enumerate(counts)]
+    want = []
+    for sc in scenes:
+        g = {k: t.cuda() for k, t in sc.items()}
+        want.append(pipe(g["triangles"], g["texture"], g["mask"], g["vn"], g["c2w"], g["fov"], resolution=64).cpu())
+    pipe.cuda_graphs = True
+    host = [{k: t.pin_memory() for k, t in sc.items()} for sc in scenes]
+    got = [img.clone() for img in pipe.render_stream(iter(host), resolution=64, pad_to=128)]
+    assert len(pipe._graphs) == 1, "every padded scene must replay the same graph"
+    for a, b, n in zip(got, want, counts):
+        assert a.shape == b.shape
+        assert hdr_rel_err(a, b) < 2e-3, f"{n} triangles padded to 128"
+    with pytest.raises(ValueError):
+        list(pipe.render_stream(iter(host), resolution=64, pad_to=64))
+
+
 def test_cbox_scene_and_constant_texture_fast_path(golden_dir):
     """BASELINE configs[0/1] geometry: the converted examples/cbox.json (5633 triangles) renders within
     tolerance of the fp32 oracle, and the constant-texture fast path ([B,N,13] input, texel-summed
@@ -120,7 +143,7 @@ def test_cbox_scene_and_constant_texture_fast_path(golden_dir):
     pipe, sd = _pipe(cfg, 13)
     scene = sio.load_npz(os.path.join(golden_dir, "cbox_scene.npz"))
     full = sio.to_pipeline_inputs(scene)
-    _check(pipe, sd, cfg, full, 64, "cbox full texture")
+    oracle = _check(pipe, sd, cfg, full, 64, "cbox full texture")
     g = {k: v.cuda() for k, v in full.items()}
     ref = pipe(g["triangles"], g["texture"], g["mask"], g["vn"], g["c2w"], g["fov"], resolution=64)
     const = {k: v.cuda() for k, v in sio.to_pipeline_inputs(scene, constant_texture=True).items()}
@@ -129,6 +152,10 @@ def test_cbox_scene_and_constant_texture_fast_path(golden_dir):
     rel, psnr = hdr_rel_err(fast, ref), log_psnr(fast, ref)
     print(f"constant-texture path vs texel path: hdr rel {rel:.3e} log-PSNR {psnr:.1f} dB")
     assert rel <= 5e-3 and psnr >= 55.0
+    # and directly against the fp32 oracle (which sees the full 32 x 32 texel grid)
+    rel_o, psnr_o = hdr_rel_err(fast, oracle), log_psnr(fast, oracle)
+    print(f"constant-texture path vs oracle: hdr rel {rel_o:.3e} log-PSNR {psnr_o:.1f} dB")
+    assert rel_o <= REL_TOL and psnr_o >= PSNR_MIN
 
 
 def test_cuda_graph_replay_matches_eager():
@@ -147,6 +174,16 @@ def test_cuda_graph_replay_matches_eager():
     assert len(pipe._graphs) == 2 and pipe.replayed_launches > 0
     for a, b in zip(graphed, eager + [eager[0]]):
         assert torch.equal(a, b)
+    # results of consecutive replays of one graph stay valid without the caller copying them ...
+    def raw(sc):
+        return pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=64)
+    r1, r2 = raw(scenes[0]), raw(scenes[1])
+    assert r1.data_ptr() != r2.data_ptr() and torch.equal(r1, eager[0]) and torch.equal(r2, eager[1])
+    # ... unless the static output itself is requested
+    pipe.graph_static_outputs = True
+    s1 = raw(scenes[0])
+    s2 = raw(scenes[1])
+    assert s1.data_ptr() == s2.data_ptr() and torch.equal(s2, eager[1])
 
 
 def test_ldr_quantize_bit_exact_and_streamed():
