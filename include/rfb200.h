@@ -236,6 +236,11 @@ int rfb_pack_mask(const uint8_t* mask, uint32_t* bits, int n, int n_prefix, int 
 
 int rfb_cast(const float* x, void* out, int out_dtype, long long n, rfb_stream_t stream);
 
+/* out[c*ld_out + r] = in[r*ld_in + c] for 16-bit elements (cols, ld_in, ld_out even).  The row-sharded scene stage
+ * (renderformer_b200/engine.py:_encode_scene_sharded) all-gathers the ranks' [k | v] rows and turns V into the
+ * V^T layout rfb_attention reads; the single-GPU path never needs it (its V leaves the GEMM transposed). */
+int rfb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols, rfb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * DPT decoder helpers, NHWC f16 (layers/dpt.py:154-155,195-213).
  * ------------------------------------------------------------------------------- */

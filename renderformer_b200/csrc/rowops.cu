@@ -509,6 +509,35 @@ __global__ void cast_kernel(const float* __restrict__ x, void* __restrict__ out,
   }
 }
 
+// 16-bit matrix transpose out[c][r] = in[r][c] through a padded 64 x 64 shared-memory tile: 32-bit (two-element)
+// accesses on both sides, 128 contiguous bytes per warp row.  Used by the row-sharded scene stage: V arrives
+// row-major from the all-gather of the ranks' [k | v] rows and the attention kernels want V^T (keys contiguous).
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, long long ld_in,
+                                                          uint16_t* __restrict__ out, long long ld_out, int rows, int cols) {
+  __shared__ uint16_t tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx * 2;
+    uint32_t v = 0;
+    if (r < rows && c < cols) v = *reinterpret_cast<const uint32_t*>(in + (long long)r * ld_in + c);  // cols even
+    tile[ty + i * 8][tx * 2] = static_cast<uint16_t>(v & 0xffffu);
+    tile[ty + i * 8][tx * 2 + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx * 2;  // output row = input column
+    if (c < cols && r < rows) {
+      const uint32_t v = static_cast<uint32_t>(tile[tx * 2][ty + i * 8]) |
+                         (static_cast<uint32_t>(tile[tx * 2 + 1][ty + i * 8]) << 16);
+      if (r + 1 < rows) *reinterpret_cast<uint32_t*>(out + (long long)c * ld_out + r) = v;
+      else out[(long long)c * ld_out + r] = static_cast<uint16_t>(v & 0xffffu);
+    }
+  }
+}
+
 }  // namespace rfb
 
 using namespace rfb;
@@ -554,6 +583,16 @@ extern "C" int rfb_qknorm_rope(const float* x, long long ldx, int in_period, con
   qknorm_rope_kernel<<<src_rows, kRopeViews * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq, out_dtype);
   RFB_LAUNCHED("qknorm_rope_kernel");
+}
+
+extern "C" int rfb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols,
+                               rfb_stream_t stream) {
+  if (!in || !out || rows <= 0 || cols <= 0 || cols % 2 || ld_in % 2 || ld_out % 2 || ld_in < cols || ld_out < rows)
+    return RFB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) return RFB_ERR_ALIGN;
+  transpose16_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols);
+  RFB_LAUNCHED("transpose16_kernel");
 }
 
 extern "C" int rfb_qknorm_rope_table(const float* x, long long ldx, const float* w, void* out, int out_dtype,

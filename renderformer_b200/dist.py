@@ -63,34 +63,60 @@ def broadcast_scene_state(state: SceneState, src: int = 0) -> SceneState:
     return state
 
 
-def gather_images(img: torch.Tensor, dst: int = 0, sizes: Optional[List[int]] = None):
+class GatherHandle:
+    """Result of an image gather that may still be in flight (`gather_images(..., async_op=True)`): `wait()`
+    makes the current stream wait for it and returns the gathered stack on `dst`, None elsewhere."""
+
+    def __init__(self, work, full, sizes, vmax, keep):
+        self.work, self.full, self.sizes, self.vmax, self.keep = work, full, sizes, vmax, keep
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        self.keep = None
+        if self.full is None:
+            return None
+        if all(n == self.vmax for n in self.sizes):
+            return self.full  # the receive buffers are slices of one tensor: no concatenation
+        return torch.cat([self.full[r * self.vmax:r * self.vmax + n] for r, n in enumerate(self.sizes)], dim=0)
+
+
+def gather_images(img: torch.Tensor, dst: int = 0, sizes: Optional[List[int]] = None, async_op: bool = False):
     """Gather per-rank image stacks [V_r, H, W, 3] on `dst` (returns the concatenation there, None
-    elsewhere).  `sizes` lists V_r per rank when the split is uneven."""
+    elsewhere).  `sizes` lists V_r per rank when the split is uneven.  With `async_op` the collective is only
+    enqueued (on NCCL's own stream, behind the work already queued on the current stream) and a GatherHandle
+    is returned: the caller may go on launching the next job and `wait()` later; `img` must not be overwritten
+    before that (pass a copy when it is the static output of a CUDA graph)."""
     world, rank = _world()
     if world == 1:
-        return img
+        return GatherHandle(None, img, [img.shape[0]], img.shape[0], None) if async_op else img
     if sizes is None:
         sizes = [img.shape[0]] * world
     vmax = max(sizes)
     pad = img
     if img.shape[0] < vmax:
         pad = torch.cat([img, img.new_zeros((vmax - img.shape[0],) + tuple(img.shape[1:]))], dim=0)
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad.contiguous(), bufs, dst=dst)
-    if rank != dst:
-        return None
-    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+    pad = pad.contiguous()
+    full = torch.empty((world * vmax,) + tuple(pad.shape[1:]), dtype=pad.dtype, device=pad.device) if rank == dst else None
+    bufs = list(full.split(vmax, dim=0)) if rank == dst else None
+    work = dist.gather(pad, bufs, dst=dst, async_op=True)
+    handle = GatherHandle(work, full, sizes, vmax, pad)
+    return handle if async_op else handle.wait()
 
 
 @torch.no_grad()
 def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int = 512, dst: Optional[int] = 0,
-                   texture_own_rows: bool = False, torch_dtype: torch.dtype = torch.float16):
+                   texture_own_rows: bool = False, torch_dtype: torch.dtype = torch.float16, async_gather: bool = False):
     """`RenderFormerRenderingPipeline.render` on all ranks of the process group: every rank passes the
     SAME scene and the full camera list c2w [B,V,4,4] / fov [B,V,1]; the scene stage is row-sharded, each
     rank renders `view_slice(V)`, and the images are gathered on `dst` (returns [B,V,H,W,3] there and
     None elsewhere; `dst=None` skips the gather and returns this rank's [B,V_rank,H,W,3]).  With
     `pipe.cuda_graphs` and device inputs the whole per-rank schedule, NCCL all-gathers included, is one
-    CUDA-graph replay."""
+    CUDA-graph replay.  `async_gather` (one scene per call): the image gather is only enqueued and a
+    GatherHandle is returned on every rank -- a caller rendering job after job lets the gather of job k
+    travel over NVLink while the scene stage of job k+1 runs, and calls `handle.wait()` before using the
+    images (at the latest before the job after next)."""
     world, rank = _world()
     V = c2w.shape[1]
     mine = view_slice(V, world, rank)
@@ -115,6 +141,9 @@ def render_sharded(pipe, triangles, texture, mask, vn, c2w, fov, resolution: int
         return img
     sizes = [view_slice(V, world, r).stop - view_slice(V, world, r).start for r in range(world)]
     B = img.shape[0]
+    if async_gather and B == 1:
+        # a private copy: `img` may be the static output of a CUDA graph that the next call replays
+        return gather_images(img[0].clone(), dst=dst, sizes=sizes, async_op=True)
     out = gather_images(img.transpose(0, 1).contiguous() if B > 1 else img[0], dst=dst, sizes=sizes)
     if out is None:
         return None

@@ -377,6 +377,8 @@ class Engine:
                           vt_rows_per_batch=Ntp, **nrm)
             qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((rows, 2 * d), bf), rows=rows, d=d, nseg=2,
                                   ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
+            if taps is not None:  # per-layer 16-bit K (after QK-norm + RoPE) and V^T: what the sharded schedule gathers
+                taps.setdefault("enc_kv", []).append((qkr[:, d:].clone(), vt.clone()))
             att = self._e((rows, d), bf)
             ops.attention(qkr, qkr[:, d:], vt, att, B=B, H=H, Nq=Ntp, Nk=Ntp, ldq=2 * d, ldk=2 * d, ldvt=Ntp, ldo=d,
                           q_bs=Ntp * 2 * d, k_bs=Ntp * 2 * d, vt_bs=d * Ntp, o_bs=Ntp * d, mask_bits=bits,
@@ -429,12 +431,13 @@ class Engine:
     def _encode_scene_sharded(self, triangles, texture, mask, vn, texture_is_log, sh: RowShard,
                               texture_own_rows: bool = False, gather_seq: bool = False) -> SceneState:
         """One scene, token rows split over the ranks of `sh` (see RowShard).  Per layer and rank:
-        [q|k|v] projection of ALL rows from the gathered 16-bit stream (K and V are needed for every
-        key; 26 GFLOP, replicated), QK-norm + RoPE, attention of the OWN query rows against all keys,
-        out-projection + SwiGLU on the own rows, then one all-gather of the own rows' 16-bit copy and
-        row sums of squares.  Row r of the gathered buffer is [d bf16 | d/128 fp32 partial sums | pad],
-        so a single collective moves both.  The arithmetic of a row does not depend on which rank owns
-        it: the result is bit-identical to the single-GPU schedule (tests/test_dist_gpu.py)."""
+        [q|k|v] projection, QK-norm and RoPE of the OWN rows, one all-gather of every rank's 16-bit [k | v]
+        rows (16.8 MB for 4096 triangles), a local transpose of V, attention of the own query rows against
+        all keys, out-projection + SwiGLU on the own rows.  Nothing is computed twice; after the last layer
+        one more gather collects the 16-bit stream + row sums that the hoisted decoder K / V are projected
+        from (replicated: 0.2 TFLOP is cheaper than moving the 300 MB result).  The arithmetic of a row does
+        not depend on which rank owns it: the result is bit-identical to the single-GPU schedule
+        (tests/test_dist_gpu.py)."""
         cfg, w, dev = self.cfg, self.w, self.device
         N = triangles.shape[1]
         d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
@@ -486,32 +489,48 @@ class Engine:
         words = 4 * ((Ntp + 127) // 128)
         bits = ops.pack_mask(mask_u8, self._e((1, words), torch.int32), n=N, n_prefix=nreg, words=words, batch=1)
 
-        # ---- gathered 16-bit stream + row sums of squares
+        # ---- per layer every rank projects, normalises and rotates ITS rows, then ONE all-gather moves the 16-bit
+        # [k | v] rows of all ranks (row r of `kv` = [d k | d v]); V is transposed locally for the attention kernel
+        S_ = S
+        kv = self._e((sh.world * S_, 2 * d), bf)
+        kv_chunk = kv[sh.rank * S_:(sh.rank + 1) * S_]
+        nrm = dict(norm_dim=d, norm_eps=EPS)
+        n_own = max(rows, 1)
+        xb, xsq = self._e((n_own, d), bf), self._e((n_own, P), f32)
+        xb2, xsq2 = self._e((n_own, d), bf), self._e((n_own, P), f32)
+        qk32 = self._e((n_own, 2 * d), f32)
+        qr = self._e((n_own, d), bf)
+        att = self._e((n_own, d), bf)
+        vt = self._e((1, d, Ntp), bf)
+        if rows > 0:
+            ops.rowstat(x, xb, xsq, rows=rows, d=d)
+        for i in range(cfg.num_layers):
+            o = f"enc{i}."
+            wqkv = w[o + "wqkv"]
+            if rows > 0:
+                ops.gemm(xb[:rows], wqkv[:2 * d], out=qk32, in_sumsq=xsq[:rows], **nrm)                 # q | k, fp32
+                ops.gemm(xb[:rows], wqkv[2 * d:], out=kv[r0:r1, d:], in_sumsq=xsq[:rows], **nrm)       # v -> 16 bit
+                ops.qknorm_rope(qk32, w[o + "qkn"][:d], qr, rows=rows, d=d, nseg=1, ldx=2 * d, ldo=d, pos=pos[r0:r1],
+                                freqs=w["enc.freqs"], eps=EPS)
+                ops.qknorm_rope(qk32[:, d:], w[o + "qkn"][d:], kv[r0:r1], rows=rows, d=d, nseg=1, ldx=2 * d, ldo=2 * d,
+                                pos=pos[r0:r1], freqs=w["enc.freqs"], eps=EPS)
+            sh.all_gather(kv, kv_chunk)
+            ops.transpose16(kv[:Ntp, d:], vt[0], rows=Ntp, cols=d)
+            if rows > 0:
+                ops.attention(qr, kv, vt, att, B=1, H=H, Nq=rows, Nk=Ntp, ldq=d, ldk=2 * d, ldvt=Ntp, ldo=d,
+                              mask_bits=bits, mask_bs=words)
+                ops.gemm(att[:rows], w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2, M=rows)
+                g = ops.gemm(xb2[:rows], w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2[:rows], **nrm)
+                ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb, M=rows)
+        # the hoisted decoder K / V need the final 16-bit stream + row sums of ALL rows: one more gather
+        # (row r of `xbs` = [d 16-bit values | d/128 fp32 partial sums | pad])
         xbs = self._e((sh.world * S, ldx), bf)
         xbs32 = xbs.view(f32)                                        # [world*S, ldx/2]
         xb_all, xsq_all = xbs[:Ntp, :d], xbs32[:Ntp, d // 2:d // 2 + P]
-        xb_own, xsq_own = xbs[r0:r1, :d], xbs32[r0:r1, d // 2:d // 2 + P]
-        chunk = xbs[sh.rank * S:(sh.rank + 1) * S]
-        nrm = dict(norm_dim=d, norm_eps=EPS)
         if rows > 0:
-            ops.rowstat(x, xb_own, xsq_own, rows=rows, d=d)
-            xb2, xsq2 = self._e((rows, d), bf), self._e((rows, P), f32)
-            att = self._e((rows, d), bf)
-        sh.all_gather(xbs, chunk)
-        for i in range(cfg.num_layers):
-            o = f"enc{i}."
-            vt = self._e((1, d, Ntp), bf)
-            qk = ops.gemm(xb_all, w[o + "wqkv"], out=self._e((Ntp, 2 * d), f32), in_sumsq=xsq_all, vt_out=vt,
-                          vt_split=2 * d, vt_rows_per_batch=Ntp, **nrm)
-            qkr = ops.qknorm_rope(qk, w[o + "qkn"], self._e((Ntp, 2 * d), bf), rows=Ntp, d=d, nseg=2,
-                                  ldx=2 * d, ldo=2 * d, pos=pos, freqs=w["enc.freqs"], eps=EPS)
-            if rows > 0:
-                ops.attention(qkr[r0:r1], qkr[:, d:], vt, att, B=1, H=H, Nq=rows, Nk=Ntp, ldq=2 * d, ldk=2 * d,
-                              ldvt=Ntp, ldo=d, mask_bits=bits, mask_bs=words)
-                ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2, M=rows)
-                g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
-                ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq_own, out16=xb_own, M=rows)
-            sh.all_gather(xbs, chunk)
+            xbs[r0:r1, :d].copy_(xb[:rows])
+            xbs32[r0:r1, d // 2:d // 2 + P].copy_(xsq[:rows])
+        sh.all_gather(xbs, xbs[sh.rank * S:(sh.rank + 1) * S])
         # hoisted decoder K / V of ALL layers from the gathered stream, replicated on every rank (0.2 TFLOP:
         # cheaper than moving the 300 MB result over NVLink)
         k_all, v_all = self.hoist_kv(xb_all, xsq_all, 1, Ntp)

@@ -69,7 +69,7 @@ class AttnArgs(C.Structure):
 SYMBOLS = [
     "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope", "rfb_qknorm_rope_table",
     "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_ray_map_tokens", "rfb_ray_map", "rfb_positions",
-    "rfb_pack_mask", "rfb_cast", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear", "rfb_ldr_quantize",
+    "rfb_pack_mask", "rfb_cast", "rfb_transpose16", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear", "rfb_ldr_quantize",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
         "rfb_positions": [p, p, p, p, i, i, i, i, p],
         "rfb_pack_mask": [p, p, i, i, i, i, p],
         "rfb_cast": [p, p, i, ll, p],
+        "rfb_transpose16": [p, ll, p, ll, i, i, p],
         "rfb_pixel_shuffle": [p, p, i, i, i, i, i, p],
         "rfb_im2col_s2": [p, p, i, i, i, i, p],
         "rfb_upsample_bilinear": [p, p, i, i, i, i, i, i, p],

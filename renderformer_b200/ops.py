@@ -268,6 +268,14 @@ def cast(x, out):
     return out
 
 
+def transpose16(x, out, *, rows, cols):
+    """out[c, r] = x[r, c] for 16-bit 2-D (possibly strided) tensors."""
+    _need_cuda(x, out)
+    L.check(_timed("transpose16", 0.0, lambda: L.load().rfb_transpose16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0),
+                                                                        rows, cols, _stream())), "rfb_transpose16")
+    return out
+
+
 def pixel_shuffle(x, out, *, B, h, w, s, C_):
     _need_cuda(x, out)
     L.check(_timed("pixel_shuffle", 0.0, lambda: L.load().rfb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, h, w, s, C_, _stream())), "rfb_pixel_shuffle")

@@ -1,8 +1,9 @@
 """GPU: the multi-GPU data plane.
 
 * `test_row_sharded_encoder_emulated`: ONE GPU.  The row-sharded view-independent stage of every rank
-  of a world of W is run in turn; its all-gather is replaced by the per-layer streams recorded from the
-  single-GPU schedule, and what the rank contributes is compared bit for bit with the recorded rows.
+  of a world of W is run in turn; its all-gathers are replaced by the per-layer K / V (and the final 16-bit
+  stream) recorded from the single-GPU schedule, and what the rank contributes is compared bit for bit
+  with the recorded rows.
   Rank r's arithmetic never sees which device computed the other rows, so this pins the sharded
   schedule without needing W devices.
 * `test_sharded_render_equals_single_gpu`: TWO (or more) GPUs, `torch.distributed.run`, NCCL.  The
@@ -48,31 +49,36 @@ def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world):
     sc = {k: v.cuda() for k, v in make_scene(n_tris, 1, seed=11, pad_to=pad_to).items()}
     taps = {}
     ref = eng.encode_scene(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], taps=taps)
-    stream = taps["enc_stream"]                     # (xb [Ntp,d] bf16, xsq [Ntp,P] fp32) per gather point
+    xb_fin, xsq_fin = taps["enc_stream"][-1]        # final 16-bit stream + row sums (input of the K/V hoist)
+    enc_kv = taps["enc_kv"]                         # per layer: K [Ntp,d] after QK-norm + RoPE, V^T [1,d,Ntp]
     d = cfg.latent_dim
     P = d // 128
-    assert len(stream) == cfg.num_layers + 1
+    assert len(enc_kv) == cfg.num_layers
     for rank in range(world):
         step = [0]
 
         def fake_all_gather(full, chunk, rank=rank):
-            if full.dtype == torch.float32:         # the final fp32 token gather
-                S = full.shape[0] // world
-                mine = full[rank * S:(rank + 1) * S].clone()
-                full[:ref.Ntp].copy_(ref.seq[0])
-                r0, r1 = min(rank * S, ref.Ntp), min((rank + 1) * S, ref.Ntp)
-                assert torch.equal(mine[:r1 - r0], ref.seq[0, r0:r1]), f"rank {rank}: own fp32 rows differ"
-                return
-            xb, xsq = stream[step[0]]
             S = full.shape[0] // world
             r0, r1 = min(rank * S, ref.Ntp), min((rank + 1) * S, ref.Ntp)
-            f32 = full.view(torch.float32)
-            own_b = full[r0:r1, :d].clone()
-            own_s = f32[r0:r1, d // 2:d // 2 + P].clone()
-            assert torch.equal(own_b, xb[r0:r1]), f"rank {rank} gather {step[0]}: 16-bit rows differ"
-            assert torch.equal(own_s, xsq[r0:r1]), f"rank {rank} gather {step[0]}: row sums differ"
-            full[:ref.Ntp, :d].copy_(xb)            # what the other ranks would have contributed
-            f32[:ref.Ntp, d // 2:d // 2 + P].copy_(xsq)
+            if full.dtype == torch.float32:         # the optional fp32 token gather
+                mine = full[rank * S:(rank + 1) * S].clone()
+                full[:ref.Ntp].copy_(ref.seq[0])
+                assert torch.equal(mine[:r1 - r0], ref.seq[0, r0:r1]), f"rank {rank}: own fp32 rows differ"
+                return
+            if step[0] < cfg.num_layers:            # per-layer gather of the ranks' [k | v] rows
+                k, vt = enc_kv[step[0]]
+                v = vt[0].t()                       # [Ntp, d]
+                assert full.shape[1] == 2 * d
+                assert torch.equal(full[r0:r1, :d], k[r0:r1]), f"rank {rank} layer {step[0]}: own K rows differ"
+                assert torch.equal(full[r0:r1, d:], v[r0:r1]), f"rank {rank} layer {step[0]}: own V rows differ"
+                full[:ref.Ntp, :d].copy_(k)         # what the other ranks would have contributed
+                full[:ref.Ntp, d:].copy_(v)
+            else:                                   # final gather: 16-bit stream + row sums of squares
+                f32 = full.view(torch.float32)
+                assert torch.equal(full[r0:r1, :d], xb_fin[r0:r1]), f"rank {rank}: final 16-bit rows differ"
+                assert torch.equal(f32[r0:r1, d // 2:d // 2 + P], xsq_fin[r0:r1]), f"rank {rank}: final row sums differ"
+                full[:ref.Ntp, :d].copy_(xb_fin)
+                f32[:ref.Ntp, d // 2:d // 2 + P].copy_(xsq_fin)
             step[0] += 1
 
         sh = RowShard(rank, world, fake_all_gather)
