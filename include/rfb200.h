@@ -155,9 +155,18 @@ typedef struct {
   int norm_dim;
   float norm_eps;
   int dtype; /* operand type of Q, K, Vt and O: RFB_BF16 (also 0 = unset) or RFB_F16 */
+  /* key splitting (mode 0, optional; 0 = off): the key range is cut into chunks of kv_split_tiles 128-key tiles,
+   * every chunk runs on its own CTA (more CTAs when there are few query rows, e.g. one rank's rows of the
+   * row-sharded scene stage) and a second kernel merges the chunks' partial softmax results in chunk order.
+   * The result of a query row depends on kv_split_tiles but not on how many rows the call holds.
+   * split_ws: caller-provided scratch, >= rfb_attention_ws_bytes(...) bytes, 16-byte aligned; at most 8 chunks. */
+  int kv_split_tiles;
+  void* split_ws;
+  long long split_ws_bytes;
 } rfb_attn_args;
 
 int rfb_attention(const rfb_attn_args* a, rfb_stream_t stream);
+long long rfb_attention_ws_bytes(int B, int H, int Nq, int Nk, int kv_split_tiles);
 
 /* ---------------------------------------------------------------------------------
  * Row kernels (one warp per row, fp32 math, 128-bit accesses).
@@ -182,6 +191,18 @@ int rfb_rowstat(const float* x, void* out16, int out_dtype, long long ld16, floa
 int rfb_qknorm_rope(const float* x, long long ldx, int in_period, const float* w, void* out, int out_dtype,
                     long long ldo, int rows, int d, int nseg, float eps, const float* pos, const float* freqs,
                     int nfreq, rfb_stream_t stream);
+
+/* Row-sharded scene stage (multi-GPU; the reference has no counterpart, models/renderformer.py:171-206 runs on one
+ * device): post-processing of ONE rank's fused [q | k | v] projection x fp32 [rows, ldx >= 3d] (RMSNorm row factor
+ * applied) fused with the layer's all-gather.  q and k get the QK-RMSNorm (w_qk = [w_q | w_k]) + triangle RoPE of
+ * rfb_qknorm_rope (bit-identical per row), v is cast; q goes to out_q [rows, ldq], k | v go to row row0 + r of
+ * EVERY destination [*, ldkv] (columns [0,d) and [d,2d)).  kv_dst: n_dst (<= 8) device pointers -- this rank's own
+ * store, plus the peer-mapped stores of the other ranks (plain NVLink stores) -- or, with multicast != 0, ONE NVLS
+ * multicast address (multimem.st: the switch replicates each store into all ranks' memories).  The caller
+ * synchronises the ranks afterwards (a signal-pad barrier) before anybody reads the stores. */
+int rfb_qkv_post(const float* x, long long ldx, const float* w_qk, void* out_q, long long ldq, void* const* kv_dst,
+                 int n_dst, int multicast, long long ldkv, long long row0, int rows, int d, float eps, const float* pos,
+                 const float* freqs, int nfreq, int out_dtype, rfb_stream_t stream);
 
 /* The same with READY-MADE rotation tables, as MultiHeadAttention.forward receives them (layers/attention.py:115:
  * rope_cos / rope_sin [rows, ldtab >= 64] fp32 from freqs_to_cos_sin, encodings/rope.py:78-103): pair (i, i+64) of

@@ -40,6 +40,10 @@ struct Attn3Params {
   const float* q_sumsq;
   int sumsq_ld, sumsq_parts;
   float inv_norm_dim, norm_eps;
+  // key splitting, as in attention2.cu (the two kernels leave bit-identical partial results)
+  int B, split_tiles;
+  float* part_o;
+  float* part_ml;
 };
 
 constexpr uint32_t kT3 = 128 * 128 * 2;  // 128 x 128 bf16 tile
@@ -84,8 +88,11 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y;
+  const int split = p.split_tiles > 0 ? blockIdx.z / p.B : 0;
+  const int b = blockIdx.z - split * p.B;
   const int q0 = blockIdx.x * 128;
+  const int j_begin = split * p.split_tiles;  // first key tile of this CTA
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStg3; ++i) {
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tO = tmem_base + 256, tQ = tmem_base + 384;
-  const int n_tiles = p.n_kv_tiles;
+  const int n_tiles = p.split_tiles > 0 ? min(p.split_tiles, p.n_kv_tiles - j_begin) : p.n_kv_tiles;
   const int kb = p.k_batched ? b : 0;
   const int vb = p.v_batched ? b : 0;
 
@@ -118,12 +125,13 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
         const uint32_t ph = (j / kStg3) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_expect_tx(&k_full[s], kT3);
-        tma_load_3d(sK + s * kT3, &tmK, &k_full[s], h * 128, j * 128, kb);
-        tma_load_3d(sK + s * kT3 + kH3, &tmK, &k_full[s], h * 128 + 64, j * 128, kb);
+        const int key0 = (j_begin + j) * 128;
+        tma_load_3d(sK + s * kT3, &tmK, &k_full[s], h * 128, key0, kb);
+        tma_load_3d(sK + s * kT3 + kH3, &tmK, &k_full[s], h * 128 + 64, key0, kb);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_expect_tx(&v_full[s], kT3);
-        tma_load_3d(sV + s * kT3, &tmV, &v_full[s], j * 128, h * 128, vb);
-        tma_load_3d(sV + s * kT3 + kH3, &tmV, &v_full[s], j * 128 + 64, h * 128, vb);
+        tma_load_3d(sV + s * kT3, &tmV, &v_full[s], key0, h * 128, vb);
+        tma_load_3d(sV + s * kT3 + kH3, &tmV, &v_full[s], key0 + 64, h * 128, vb);
       }
     }
   } else if (warp == 1) {
@@ -205,10 +213,10 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
     for (int j = 0; j < n_tiles; ++j) {
       uint32_t mw[4];
       if (p.mask_bits) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.mask_bits + static_cast<long long>(b) * p.mask_stride_words + j * 4));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.mask_bits + static_cast<long long>(b) * p.mask_stride_words + (j_begin + j) * 4));
         mw[0] = u.x, mw[1] = u.y, mw[2] = u.z, mw[3] = u.w;
       } else {
-        const int rem = p.Nk - j * 128;
+        const int rem = p.Nk - (j_begin + j) * 128;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const int lo = w * 32;
@@ -288,12 +296,38 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
+      // A parity wait can only tell the current phase of a barrier from the one before it.  S is double-buffered,
+      // so a fast warp may get here a whole tile ahead of the slowest one: P_{j-1} V_{j-1} is then not even issued
+      // and pv_done still sits in phase j-1 -- the epilogue's wait for phase j (same parity as phase j-2, which HAS
+      // completed) would fall through and read O two products early.  Seeing phase j-1 complete first makes the
+      // epilogue's wait unambiguous (S_j ready => phase j-2 complete, and phase j cannot start before this warp's
+      // arrive below).
+      if (j == n_tiles - 1 && j > 0) mbar_wait(pv_done, (j - 1) & 1);
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
 
     // epilogue: O / l -> bf16 -> global
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
+    if (p.part_o) {  // key split: un-normalised O (relative to m_run), (m_run in log2 units, l_run)
+      const long long prow = ((static_cast<long long>(split) * p.B + b) * gridDim.y + h) * p.Nq + qrow;
+      if (row_ok) {
+        float2* ml = reinterpret_cast<float2*>(p.part_ml) + prow;
+        *ml = make_float2(m_run * sl2, l_run);
+      }
+      float* po = p.part_o + prow * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tOl + c * 32, o);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(po + c * 32 + i * 4) = make_uint4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
+        }
+      }
+    } else {
     const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
     uint16_t* orow = static_cast<uint16_t*>(p.O) + static_cast<long long>(b) * p.o_batch_stride +
                      static_cast<long long>(qrow) * p.ldo + h * 128;
@@ -314,6 +348,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
         }
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -326,9 +361,12 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
 
 // called by rfb_attention (attention.cu) for mode 0
 int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_attn_args* a, int k_batched,
-                      int v_batched, cudaStream_t stream) {
+                      int v_batched, int split_tiles, int n_splits, float* part_o, float* part_ml,
+                      cudaStream_t stream) {
   if (a->ldq % 8 || (reinterpret_cast<uintptr_t>(a->Q) & 15) || (a->B > 1 && a->q_batch_stride % 8)) return RFB_ERR_ALIGN;
   Attn3Params p{};
+  p.B = a->B, p.split_tiles = n_splits > 1 ? split_tiles : 0;
+  p.part_o = n_splits > 1 ? part_o : nullptr, p.part_ml = n_splits > 1 ? part_ml : nullptr;
   p.Nq = a->Nq, p.Nk = a->Nk;
   p.n_kv_tiles = (a->Nk + 127) / 128;
   p.k_batched = k_batched, p.v_batched = v_batched;
@@ -350,7 +388,7 @@ int launch_attention3(const CUtensorMap& tmK, const CUtensorMap& tmV, const rfb_
       return RFB_ERR_LAUNCH;
     attr_set = true;
   }
-  dim3 grid((a->Nq + 127) / 128, a->H, a->B);
+  dim3 grid((a->Nq + 127) / 128, a->H, a->B * (n_splits > 1 ? n_splits : 1));
   kern<<<grid, kAttn3Threads, kAttn3Smem, stream>>>(tmK, tmV, p);
   g_launch_count++;
   return check_launch("attn3_tc_kernel");

@@ -485,10 +485,20 @@ __device__ __forceinline__ void epilogue_vt_chunks(const GemmKParams& p, uint32_
 // prefetch ping-pongs between two register sets without copies, and the sums of squares are
 // reduced across lanes once per tile instead of once per chunk.
 // ---------------------------------------------------------------------------------------------
-template <int EK>
+// x0^2 + x1^2 + x2^2 + x3^2 with the contraction pinned (the 256- and 128-wide tiles must agree bit for bit)
+__device__ __forceinline__ float sq4(const float (&x)[4]) {
+  return __fmaf_rn(x[3], x[3], __fmaf_rn(x[2], x[2], __fmaf_rn(x[1], x[1], __fmul_rn(x[0], x[0]))));
+}
+
+// NCHW = 32-column chunks per warp: 4 (BN == 256: the warp owns one whole 128-column sum-of-squares part) or
+// 2 (BN == 128: the part is shared by the two warps of a TMEM lane quarter).  In the second case the sums are
+// chained in column order -- the first-half warp (`half_idx` 0) parks its per-lane sums in its staging buffer,
+// the second-half warp adds its two chunks on top -- so every partial sum is rounded exactly as in the
+// one-warp case and a row's result does not depend on the tile width (small-M launches pick the narrow tile).
+template <int EK, int NCHW>
 __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, float* stage, int lane, uint32_t taddr,
                                                         int n_begin, int orow_mine, int arow_mine, float rs_mine,
-                                                        uint64_t* tfull_bar, uint32_t parity) {
+                                                        uint64_t* tfull_bar, uint32_t parity, int half_idx, int bar_id) {
   constexpr bool RES = ek_resid(EK);
   constexpr bool O16H = ek_half(EK);
   const int c4 = lane & 7;
@@ -502,15 +512,16 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
     rs[it] = __shfl_sync(0xffffffffu, rs_mine, it * 4 + g4);
   }
   float sqp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sqc[NCHW == 2 ? 2 : 1][8] = {};  // second-half warp of a narrow tile: its chunks' sums, added after the first half's
   const float* res = static_cast<const float*>(p.res1);
   float* out = static_cast<float*>(p.out);
   uint16_t* out16 = static_cast<uint16_t*>(p.out16);
   // the residual of the whole half tile is requested up front (register budget: setmaxnreg), so
   // its latency hides behind the main loop of this tile
-  uint4 rr4[4][8];
+  uint4 rr4[NCHW][8];
   if (RES) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NCHW; ++c)
 #pragma unroll
       for (int it = 0; it < 8; ++it)
         if (orow[it] >= 0)
@@ -519,7 +530,7 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
   mbar_wait(tfull_bar, parity);
   tc_fence_after();
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NCHW; ++c) {
     uint32_t v[32];
     tmem_ld32(taddr + c * 32, v);
     const int n = n_begin + c * 32 + c4 * 4;
@@ -548,13 +559,33 @@ __device__ __forceinline__ void epilogue_half_tile_fast(const GemmKParams& p, fl
                                       __float_as_uint(x[3]));
           *reinterpret_cast<uint4*>(out + (long long)orow[it] * p.ldo + n) = xo;
         }
-        sqp[it] += x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+        if (NCHW == 2 && half_idx == 1) sqc[NCHW == 2 ? c : 0][it] = sq4(x);
+        else sqp[it] = __fadd_rn(sqp[it], sq4(x));
         uint2 u;
         u.x = pack16<O16H>(x[0] * cm[0], x[1] * cm[1]), u.y = pack16<O16H>(x[2] * cm[2], x[3] * cm[3]);
         *reinterpret_cast<uint2*>(out16 + (long long)arow[it] * p.ld16 + n) = u;
       }
     }
     __syncwarp();
+  }
+  if (NCHW == 2) {
+    // hand-over of the first half's per-lane sums through the first-half warp's staging buffer (1 KB of it):
+    // rendezvous 1 = "sums parked", rendezvous 2 = "sums read" (the buffer is free for the next tile)
+    float* xch = (half_idx == 0 ? stage : stage - 4 * 32 * 32) + lane * 8;
+    if (half_idx == 0) {
+      *reinterpret_cast<float4*>(xch) = make_float4(sqp[0], sqp[1], sqp[2], sqp[3]);
+      *reinterpret_cast<float4*>(xch + 4) = make_float4(sqp[4], sqp[5], sqp[6], sqp[7]);
+    }
+    bar_sync(bar_id, 64);
+    if (half_idx == 1) {
+      const float4 a = *reinterpret_cast<const float4*>(xch), b = *reinterpret_cast<const float4*>(xch + 4);
+      const float first[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (orow[it] >= 0) sqp[it] = __fadd_rn(__fadd_rn(first[it], sqc[0][it]), sqc[NCHW == 2 ? 1 : 0][it]);
+    }
+    bar_sync(bar_id, 64);
+    if (half_idx == 0) return;  // the second-half warp owns the part's write
   }
   // one 128-column part per warp: reduce the 8 column lanes of every row slot, owner lane writes
   float mine = 0.f;
@@ -743,10 +774,11 @@ __global__ void __launch_bounds__(ek_resid(EK) ? kGemmThreadsWG : kGemmThreads, 
         epilogue_vt_chunks(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, n0, c_begin, c_end,
                            mt * kBM + r, valid, rs, &tfull[as], aph);
       } else if constexpr (ek_fast(EK)) {
-        static_assert(BN == 256, "specialised epilogues use the 256-wide tile");
-        epilogue_half_tile_fast<EK>(p, my_stage, lane,
-                                    tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
-                                    n0 + c_begin * 32, orow_mine, arow_mine, rs, &tfull[as], aph);
+        static_assert(BN == 256 || BN == 128, "specialised epilogues use the 256- or 128-wide tile");
+        epilogue_half_tile_fast<EK, BN / 64>(p, my_stage, lane,
+                                             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c_begin * 32,
+                                             n0 + c_begin * 32, orow_mine, arow_mine, rs, &tfull[as], aph,
+                                             (warp - EPI0) >> 2, 1 + q);
       } else {
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
         if ((p.epi == RFB_EPI_STORE) && !p.direct_store) {
@@ -1056,14 +1088,25 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   if (a->out_sumsq && (n_plain % 128 || a->out_sumsq_ld < n_plain / 128)) return RFB_ERR_ARG;
   if (a->res2 && (a->res_dtype == RFB_F32 || !a->res1)) return RFB_ERR_ARG;
 
+  // the compile-time residual-stream epilogue (EK_RESID: fp32 out = acc*r + fp32 residual, 16-bit copy, sums of
+  // squares) exists for 256- and 128-wide tiles; every other user of out_sumsq needs the 256-wide one
+  const bool resid_kind = a->epi == RFB_EPI_STORE && a->a_mode == RFB_A_LINEAR && a->N % 256 == 0 && a->out16 &&
+                          a->out_sumsq && !a->bias && !a->res2 && !a->out_act && !a->vt_out && !a->col_mul &&
+                          !(a->in_rscale && a->scale_dim == 1) && a->out && a->out_dtype == RFB_F32 && a->res1 &&
+                          a->res_dtype == RFB_F32;
+  const int sms = num_sms();
+  const long long m_tiles_lin = (a->M + kBM - 1) / kBM;
   int bn = a->bn_override;
   if (a->vt_out) {
     if (bn != 0 && bn != 256) return RFB_ERR_ARG;
     bn = 256;  // vt_split is a whole number of 256-wide tiles
   }
   if (a->out_sumsq) {
-    if (bn != 0 && bn != 256) return RFB_ERR_ARG;
-    bn = 256;  // one epilogue warp per 128-column sum-of-squares part
+    if (bn != 0 && bn != 256 && !(bn == 128 && resid_kind)) return RFB_ERR_ARG;
+    // one epilogue warp per 128-column sum-of-squares part; a launch that cannot fill half of the SMs with
+    // 256-wide tiles (the row-sharded scene stage: a few hundred rows per rank) takes the 128-wide variant,
+    // whose two warps per part chain their sums in column order -- bit-identical results
+    if (bn == 0) bn = (resid_kind && m_tiles_lin * (a->N / 256) * 2 <= sms) ? 128 : 256;
   }
   if (bn == 0) {
     if (a->N <= 32) bn = 32;
@@ -1072,6 +1115,17 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
     else if (a->a_mode == RFB_A_LINEAR && a->N > 1024 && ((a->N + 255) / 256) * 256 * 100 <= a->N * 110)
       bn = 256;  // ragged N: the 256-wide UMMA is ~35 % faster per FLOP, worth <= 10 % padded columns
     else bn = 128;
+    // Small grids (few rows): a narrower tile puts more SMs to work.  cost = rounds of the persistent grid x
+    // (tile width + a fixed per-tile share for the pipeline fill and the slower narrow UMMA); the accumulation
+    // order along K does not depend on the tile width, so the result is bit-identical whichever is picked.
+    if (bn == 256 && a->a_mode == RFB_A_LINEAR && (a->epi == RFB_EPI_STORE || a->epi == RFB_EPI_SWIGLU)) {
+      long long best = -1;
+      for (int cand = 256; cand >= 64; cand >>= 1) {
+        const long long tiles = m_tiles_lin * (a->N / cand);
+        const long long cost = ((tiles + sms - 1) / sms) * (cand + 64);
+        if (best < 0 || cost < best) best = cost, bn = cand;
+      }
+    }
   }
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RFB_ERR_ARG;
 
@@ -1194,6 +1248,11 @@ extern "C" int rfb_gemm(const rfb_gemm_args* a, rfb_stream_t stream_) {
   int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
   int grid = (int)(total < cap ? total : cap);
 
+  if (bn == 128 && a->out_sumsq) {  // narrow residual-stream tile (resid_kind checked above)
+    if (p.direct_store) return RFB_ERR_ARG;
+    return a->out16_dtype == RFB_F16 ? launch_gemm<128, EK_RESID_H>(tmA, tmB, p, grid, stream)
+                                     : launch_gemm<128, EK_RESID>(tmA, tmB, p, grid, stream);
+  }
   if (bn == 256 && a->N % 256 == 0 && a->epi == RFB_EPI_STORE && !p.direct_store && a->out16 &&
       a->out_sumsq && !a->bias && !a->res2 && !a->out_act && !(a->in_rscale && a->scale_dim == 1)) {
     const bool half = a->out16_dtype == RFB_F16;

@@ -217,6 +217,12 @@ __device__ __forceinline__ void tmem_wait_st() {
 // ----------------------------------------------------------------------------
 // register re-distribution between warpgroups (all 4 warps of a warpgroup execute it)
 // ----------------------------------------------------------------------------
+// named barrier: rendezvous of `count` threads (a multiple of 32) on hardware barrier `id` (1..15;
+// 0 is __syncthreads); orders the participants' shared-memory accesses like __syncthreads does
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));

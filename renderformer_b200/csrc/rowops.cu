@@ -109,6 +109,69 @@ __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
   __sincosf(r, &s, &c);
 }
 
+// cos / sin of the four rotation pairs [o, o+4) a lane owns inside every head (pair i < 9*nfreq rotates by
+// pos[i / nfreq] * freq[i % nfreq], the rest are the identity); `prow` = the row's 9 position floats or NULL
+__device__ __forceinline__ void rope_lane_cs(const float* __restrict__ prow, const float* __restrict__ freqs, int nfreq,
+                                             const float* __restrict__ ctab, const float* __restrict__ stab, int o,
+                                             float (&cs)[4], float (&sn)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    cs[e] = 1.f, sn[e] = 0.f;
+    const int i = o + e;
+    if (ctab) {  // ready-made cos / sin tables (pair i rotates by entry i; entries 64.. duplicate 0..63)
+      cs[e] = ctab[i], sn[e] = stab[i];
+    } else if (prow && i < 9 * nfreq) {
+      const float ang = prow[i / nfreq] * __ldg(freqs + i % nfreq);
+      fast_sincos(ang, sn[e], cs[e]);
+    }
+  }
+}
+
+// One (row, segment) per warp: RMSNorm over the segment's d values (weight ws; NULL = rotation only) and the
+// rotation of every head's pairs (i, i+64); st(base, ra, rb) receives the rotated values of columns
+// [base, base+4) and [base+64, base+68).  Shared by every kernel that applies the QK-norm + RoPE, so that a
+// row comes out bit-identical whichever launch produced it.
+template <class St>
+__device__ __forceinline__ void qknorm_rope_segment(const float* __restrict__ xs, const float* __restrict__ ws, int d,
+                                                    float eps, const float (&cs)[4], const float (&sn)[4], int o, int lane,
+                                                    St&& st) {
+  const int units = d >> 3;  // (head, float4-pair) units per segment = H * 16
+  float4 lo[kMaxVec / 2], hi[kMaxVec / 2];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxVec / 2; ++it) {
+    const int u = it * 32 + lane;
+    if (u < units) {
+      const int base = (u >> 4) * 128 + o;
+      lo[it] = *reinterpret_cast<const float4*>(xs + base);
+      hi[it] = *reinterpret_cast<const float4*>(xs + base + 64);
+      ss += lo[it].x * lo[it].x + lo[it].y * lo[it].y + lo[it].z * lo[it].z + lo[it].w * lo[it].w;
+      ss += hi[it].x * hi[it].x + hi[it].y * hi[it].y + hi[it].z * hi[it].z + hi[it].w * hi[it].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = ws ? rsqrtf(ss / d + eps) : 1.0f;  // ws == NULL: rotation only (apply_rotary_emb_one_cossin)
+#pragma unroll
+  for (int it = 0; it < kMaxVec / 2; ++it) {
+    const int u = it * 32 + lane;
+    if (u < units) {
+      const int base = (u >> 4) * 128 + o;
+      const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 wl = ws ? __ldg(reinterpret_cast<const float4*>(ws + base)) : one4;
+      const float4 wh = ws ? __ldg(reinterpret_cast<const float4*>(ws + base + 64)) : one4;
+      const float a[4] = {lo[it].x * r * wl.x, lo[it].y * r * wl.y, lo[it].z * r * wl.z, lo[it].w * r * wl.w};
+      const float b[4] = {hi[it].x * r * wh.x, hi[it].y * r * wh.y, hi[it].z * r * wh.z, hi[it].w * r * wh.w};
+      float ra[4], rb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ra[e] = a[e] * cs[e] - b[e] * sn[e];
+        rb[e] = b[e] * cs[e] + a[e] * sn[e];
+      }
+      st(base, ra, rb);
+    }
+  }
+}
+
 // warp-per-row variant (no view fan-out): in_period == 0
 __global__ void __launch_bounds__(256, 3)
     qknorm_rope_rows_kernel(const float* __restrict__ x, long long ldx, int in_period,
@@ -122,61 +185,91 @@ __global__ void __launch_bounds__(256, 3)
   const int lane = threadIdx.x & 31;
   const long long src = in_period > 0 ? (row % in_period) : row;
   const int o = (lane & 15) * 4;  // pair offset inside a head (0..60)
-
   float cs[4], sn[4];
+  rope_lane_cs(pos ? pos + (long long)row * 9 : nullptr, freqs, nfreq, ctab ? ctab + (long long)row * ldtab : nullptr,
+               ctab ? stab + (long long)row * ldtab : nullptr, o, cs, sn);
+  const int s = blockIdx.y;  // one (row, segment) per warp: twice the warps, no serial segment loop
+  qknorm_rope_segment(x + src * ldx + (long long)s * d, w ? w + (long long)s * d : nullptr, d, eps, cs, sn, o, lane,
+                      [&](int base, const float (&ra)[4], const float (&rb)[4]) {
+                        const long long idx = (long long)row * ldo + (long long)s * d + base;
+                        store4_16(out, out_dtype, idx, ra[0], ra[1], ra[2], ra[3]);
+                        store4_16(out, out_dtype, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+                      });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-sharded scene stage: what follows a rank's fused [q | k | v] projection (fp32 [rows, 3d], the RMSNorm
+// row factor already applied) -- and the all-gather of the layer, fused into the producer:
+//   segment 0: q -> QK-RMSNorm + RoPE -> out_q [rows, ldq]                          (this rank's queries)
+//   segment 1: k -> QK-RMSNorm + RoPE -> row row0 + r, columns [0, d)   of EVERY destination
+//   segment 2: v -> cast              -> row row0 + r, columns [d, 2d)  of EVERY destination
+// The destinations are the [k | v] row stores of all ranks: either n_dst peer-mapped pointers (plain stores
+// over NVLink) or ONE NVLS multicast address (multimem.st: the NVSwitch replicates every store into all
+// ranks' memories, so a rank sends its rows once instead of once per peer).
+// ---------------------------------------------------------------------------------------------
+struct KvDst {
+  void* p[8];
+};
+
+__device__ __forceinline__ void store_kv8(const KvDst& dst, int n_dst, int multicast, long long idx, uint2 u) {
+  if (multicast) {
+    uint16_t* a = static_cast<uint16_t*>(dst.p[0]) + idx;
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(__uint_as_float(u.x)),
+                 "f"(__uint_as_float(u.y))
+                 : "memory");
+  } else {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    cs[e] = 1.f, sn[e] = 0.f;
-    const int i = o + e;
-    if (ctab) {  // ready-made cos / sin tables (pair i rotates by entry i; entries 64.. duplicate 0..63)
-      cs[e] = ctab[(long long)row * ldtab + i], sn[e] = stab[(long long)row * ldtab + i];
-    } else if (pos && i < 9 * nfreq) {
-      const float ang = pos[(long long)row * 9 + i / nfreq] * __ldg(freqs + i % nfreq);
-      fast_sincos(ang, sn[e], cs[e]);
-    }
-  }
-  const int units = d >> 3;  // (head, float4-pair) units per segment = H * 16
-  {
-    const int s = blockIdx.y;  // one (row, segment) per warp: twice the warps, no serial segment loop
-    const float* xs = x + src * ldx + (long long)s * d;
-    const float* ws = w + (long long)s * d;
-    float4 lo[kMaxVec / 2], hi[kMaxVec / 2];
-    float ss = 0.f;
-#pragma unroll
-    for (int it = 0; it < kMaxVec / 2; ++it) {
-      const int u = it * 32 + lane;
-      if (u < units) {
-        const int base = (u >> 4) * 128 + o;
-        lo[it] = *reinterpret_cast<const float4*>(xs + base);
-        hi[it] = *reinterpret_cast<const float4*>(xs + base + 64);
-        ss += lo[it].x * lo[it].x + lo[it].y * lo[it].y + lo[it].z * lo[it].z + lo[it].w * lo[it].w;
-        ss += hi[it].x * hi[it].x + hi[it].y * hi[it].y + hi[it].z * hi[it].z + hi[it].w * hi[it].w;
+    for (int i = 0; i < 8; ++i)  // static indices: the pointers stay in the kernel's parameter bank
+      if (i < n_dst) {
+        uint16_t* a = static_cast<uint16_t*>(dst.p[i]) + idx;
+        asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(a), "r"(u.x), "r"(u.y) : "memory");
       }
-    }
-    ss = warp_sum(ss);
-    const float r = w ? rsqrtf(ss / d + eps) : 1.0f;  // w == NULL: rotation only (apply_rotary_emb_one_cossin)
-#pragma unroll
-    for (int it = 0; it < kMaxVec / 2; ++it) {
-      const int u = it * 32 + lane;
-      if (u < units) {
-        const int base = (u >> 4) * 128 + o;
-        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 wl = w ? __ldg(reinterpret_cast<const float4*>(ws + base)) : one4;
-        const float4 wh = w ? __ldg(reinterpret_cast<const float4*>(ws + base + 64)) : one4;
-        const float a[4] = {lo[it].x * r * wl.x, lo[it].y * r * wl.y, lo[it].z * r * wl.z, lo[it].w * r * wl.w};
-        const float b[4] = {hi[it].x * r * wh.x, hi[it].y * r * wh.y, hi[it].z * r * wh.z, hi[it].w * r * wh.w};
-        float ra[4], rb[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ra[e] = a[e] * cs[e] - b[e] * sn[e];
-          rb[e] = b[e] * cs[e] + a[e] * sn[e];
-        }
-        const long long idx = (long long)row * ldo + (long long)s * d + base;
-        store4_16(out, out_dtype, idx, ra[0], ra[1], ra[2], ra[3]);
-        store4_16(out, out_dtype, idx + 64, rb[0], rb[1], rb[2], rb[3]);
-      }
-    }
   }
+}
+
+__device__ __forceinline__ uint2 pack4_16(int dtype, float a, float b, float c, float d) {
+  uint2 u;
+  if (dtype == RFB_BF16) u.x = pack_bf16(a, b), u.y = pack_bf16(c, d);
+  else u.x = pack_f16(a, b), u.y = pack_f16(c, d);
+  return u;
+}
+
+__global__ void __launch_bounds__(256, 3)
+    qkv_post_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w_qk,
+                    void* __restrict__ out_q, long long ldq, const __grid_constant__ KvDst dst, int n_dst, int multicast, long long ldkv,
+                    long long row0, int rows, int d, float eps, const float* __restrict__ pos,
+                    const float* __restrict__ freqs, int nfreq, int out_dtype) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.y;
+  const float* xs = x + (long long)row * ldx + (long long)s * d;
+  const long long kv_row = (row0 + row) * ldkv;
+  if (s == 2) {
+    const int nvec = d >> 7;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      if (j < nvec) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + (j * 32 + lane) * 4);
+        store_kv8(dst, n_dst, multicast, kv_row + d + (j * 32 + lane) * 4, pack4_16(out_dtype, v.x, v.y, v.z, v.w));
+      }
+    return;
+  }
+  const int o = (lane & 15) * 4;
+  float cs[4], sn[4];
+  rope_lane_cs(pos ? pos + (long long)row * 9 : nullptr, freqs, nfreq, nullptr, nullptr, o, cs, sn);
+  qknorm_rope_segment(xs, w_qk + (long long)s * d, d, eps, cs, sn, o, lane,
+                      [&](int base, const float (&ra)[4], const float (&rb)[4]) {
+                        if (s == 0) {
+                          const long long idx = (long long)row * ldq + base;
+                          store4_16(out_q, out_dtype, idx, ra[0], ra[1], ra[2], ra[3]);
+                          store4_16(out_q, out_dtype, idx + 64, rb[0], rb[1], rb[2], rb[3]);
+                        } else {
+                          store_kv8(dst, n_dst, multicast, kv_row + base, pack4_16(out_dtype, ra[0], ra[1], ra[2], ra[3]));
+                          store_kv8(dst, n_dst, multicast, kv_row + base + 64,
+                                    pack4_16(out_dtype, rb[0], rb[1], rb[2], rb[3]));
+                        }
+                      });
 }
 
 
@@ -583,6 +676,26 @@ extern "C" int rfb_qknorm_rope(const float* x, long long ldx, int in_period, con
   qknorm_rope_kernel<<<src_rows, kRopeViews * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, in_period, w, out, ldo, rows, d, nseg, eps, pos, freqs, nfreq, out_dtype);
   RFB_LAUNCHED("qknorm_rope_kernel");
+}
+
+extern "C" int rfb_qkv_post(const float* x, long long ldx, const float* w_qk, void* out_q, long long ldq,
+                            void* const* kv_dst, int n_dst, int multicast, long long ldkv, long long row0, int rows,
+                            int d, float eps, const float* pos, const float* freqs, int nfreq, int out_dtype,
+                            rfb_stream_t stream) {
+  if (!x || !w_qk || !out_q || !kv_dst || rows <= 0 || d % 128 || d > kMaxVec * 128 || ldx % 4 || ldx < 3LL * d ||
+      ldq % 4 || ldq < d || ldkv % 4 || ldkv < 2LL * d || row0 < 0 || n_dst < 1 || n_dst > 8 || (multicast && n_dst != 1))
+    return RFB_ERR_ARG;
+  if (out_dtype != RFB_BF16 && out_dtype != RFB_F16) return RFB_ERR_ARG;
+  if (pos && (!freqs || nfreq < 1 || 9 * nfreq > 64)) return RFB_ERR_ARG;
+  KvDst dst{};
+  for (int i = 0; i < n_dst; ++i) {
+    if (!kv_dst[i] || (reinterpret_cast<uintptr_t>(kv_dst[i]) & 7)) return RFB_ERR_ALIGN;
+    dst.p[i] = kv_dst[i];
+  }
+  const int wpb = 8;
+  qkv_post_kernel<<<dim3((rows + wpb - 1) / wpb, 3), wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, ldx, w_qk, out_q, ldq, dst, n_dst, multicast, ldkv, row0, rows, d, eps, pos, freqs, nfreq, out_dtype);
+  RFB_LAUNCHED("qkv_post_kernel");
 }
 
 extern "C" int rfb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols,

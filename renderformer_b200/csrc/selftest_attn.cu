@@ -49,6 +49,7 @@ struct ACase {
   const char* name;
   int B, H, Nq, Nk, mode, masked, shareKV, period;
   int fused = 0;  // 1: q_sumsq partial sums (fused q RMSNorm); 2: q and k sums (mode 1)
+  int split = 0;  // kv_split_tiles: key chunks of this many 128-key tiles + ordered merge
 };
 
 static void run(const ACase& c, bool timing_only = false) {
@@ -74,6 +75,7 @@ static void run(const ACase& c, bool timing_only = false) {
       bool ok = true;
       if (c.masked == 1) ok = k < c.Nk - 37 * (b + 1);                  // prefix (padding) mask
       if (c.masked == 2) ok = (hash_u32(k * 31 + b) % 3) != 0 || k < 16;  // arbitrary mask
+      if (c.masked == 3) ok = k < 200 - 70 * b;                         // whole key chunks without a valid key
       if (ok) hm[(size_t)b * words + k / 32] |= 1u << (k % 32);
     }
   DevBuf<uint32_t> dM(hm.size());
@@ -115,6 +117,9 @@ static void run(const ACase& c, bool timing_only = false) {
   a.mode = c.mode, a.group_id = dG.p, a.group_period = c.period;
   a.scale = 0.08838834764831845f;
   a.dtype = g_dt;
+  const long long ws_bytes = rfb_attention_ws_bytes(c.B, c.H, c.Nq, c.Nk, c.split);
+  DevBuf<float> dws((size_t)(ws_bytes / 4 + 4));
+  if (c.split) a.kv_split_tiles = c.split, a.split_ws = dws.p, a.split_ws_bytes = ws_bytes;
 
   if (timing_only) {
     for (int i = 0; i < 3; ++i) rfb_attention(&a, 0);
@@ -153,6 +158,50 @@ static void run(const ACase& c, bool timing_only = false) {
   report(c.name, got, ref, 1.5e-2, 2e-2, D);
 }
 
+// A query row's result must not depend on how many rows the call holds (which decides the kernel generation and
+// the grid): rows [r0, r0 + n) of a full-length call vs a call on those rows alone, bit for bit.
+static void run_row_invariance(const char* name, int H, int N, int r0, int n, int split) {
+  const int D = H * 128;
+  const long long ldvt = (N + 7) & ~7;
+  const size_t nq = (size_t)N * D, nv = (size_t)D * ldvt;
+  DevBuf<uint16_t> dQ(nq), dK(nq), dV(nv), dO(nq), dO2((size_t)n * D);
+  dQ.up(rand16(nq, 41, 2.0f, g_dt)), dK.up(rand16(nq, 42, 2.0f, g_dt)), dV.up(rand16(nv, 43, 1.0f, g_dt));
+  dO.fill_byte(0xff), dO2.fill_byte(0xee);
+  const int words = 4 * ((N + 127) / 128);
+  std::vector<uint32_t> hm(words, 0);
+  for (int k = 0; k < N - 29; ++k) hm[k / 32] |= 1u << (k % 32);
+  DevBuf<uint32_t> dM(hm.size());
+  dM.up(hm);
+  std::vector<uint16_t> got[2];
+  for (int w = 0; w < 2; ++w) {
+    const int Nq = w == 0 ? N : n;
+    const long long ws_bytes = rfb_attention_ws_bytes(1, H, Nq, N, split);
+    DevBuf<float> dws((size_t)(ws_bytes / 4 + 4));
+    rfb_attn_args a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1, a.H = H, a.Nq = Nq, a.Nk = N;
+    a.Q = w == 0 ? dQ.p : dQ.p + (size_t)r0 * D, a.ldq = D;
+    a.K = dK.p, a.ldk = D, a.Vt = dV.p, a.ldvt = ldvt;
+    a.O = w == 0 ? dO.p : dO2.p, a.ldo = D;
+    a.key_mask_bits = dM.p, a.mask_batch_stride_words = words;
+    a.scale = 0.08838834764831845f, a.dtype = g_dt;
+    if (split) a.kv_split_tiles = split, a.split_ws = dws.p, a.split_ws_bytes = ws_bytes;
+    int rc = rfb_attention(&a, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc != RFB_OK || e != cudaSuccess) {
+      printf("[FAIL] %-46s rc=%d cuda=%s\n", name, rc, cudaGetErrorString(e));
+      g_fail++;
+      if (e != cudaSuccess) exit(3);
+      return;
+    }
+    got[w] = w == 0 ? dO.down() : dO2.down();
+  }
+  const bool same = !memcmp(got[0].data() + (size_t)r0 * D, got[1].data(), (size_t)n * D * 2);
+  printf("[%s] %-46s rows %d..%d of %d vs alone: %s\n", same ? " ok " : "FAIL", name, r0, r0 + n, N,
+         same ? "bit-identical" : "DIFFERENT");
+  if (!same) g_fail++;
+}
+
 int main(int argc, char** argv) {
   const bool only_bench = argc > 1 && !strcmp(argv[1], "bench");
   if (const char* e = getenv("RFB_TEST_F16")) {
@@ -177,12 +226,25 @@ int main(int argc, char** argv) {
         {"swin mode1 B1 H8 N8192 period 4096", 1, 8, 8192, 8192, 1, 0, 0, 4096},
         {"fused q-norm B3 H2 Nq300 Nk400 shared KV", 3, 2, 300, 400, 0, 1, 1, 0, 1},
         {"fused q+k-norm swin mode1 B1 H2 N1024", 1, 2, 1024, 1024, 1, 0, 0, 256, 2},
+        {"key split 2 B3 H1 Nq200 Nk1000 random mask", 3, 1, 200, 1000, 0, 2, 0, 0, 0, 2},
+        {"key split 3 (3,3,2) B2 H2 Nq300 Nk1000 prefix", 2, 2, 300, 1000, 0, 1, 0, 0, 0, 3},
+        {"key split 1: chunks with no valid key", 2, 2, 300, 600, 0, 3, 0, 0, 0, 1},
+        {"key split 2 fused q-norm shared KV B3 Nk700", 3, 2, 300, 700, 0, 1, 1, 0, 1, 2},
+        {"key split 11 enc-like B1 H8 N4112", 1, 8, 4112, 4112, 0, 1, 0, 0, 0, 11},
+        {"key split 11 one rank of 8: Nq520 Nk4112", 1, 8, 520, 4112, 0, 1, 0, 0, 0, 11},
     };
     for (auto& c : cases) run(c);
+    run_row_invariance("row invariance, key split 11, H8 N4112", 8, 4112, 1040, 520, 11);
+    run_row_invariance("row invariance, no split, H8 N4112", 8, 4112, 1040, 520, 0);
+    run_row_invariance("row invariance, key split 3, H2 N1500 (ragged)", 2, 1500, 256, 200, 3);
     printf("selftest_attn: %d failure(s)\n", g_fail);
     if (g_fail) return 1;
   }
   run({"enc self  B1 H8 N4112", 1, 8, 4112, 4112, 0, 0, 0, 0}, true);
+  run({"enc self  B1 H8 N4112, key split 11", 1, 8, 4112, 4112, 0, 0, 0, 0, 0, 11}, true);
+  run({"one rank of 8: Nq520 Nk4112", 1, 8, 520, 4112, 0, 0, 0, 0}, true);
+  run({"one rank of 8: Nq520 Nk4112, key split 11", 1, 8, 520, 4112, 0, 0, 0, 0, 0, 11}, true);
+  run({"one rank of 2: Nq2056 Nk4112, key split 11", 1, 8, 2056, 4112, 0, 0, 0, 0, 0, 11}, true);
   run({"cross     B8 H8 Nq4096 Nk4112 sharedKV", 8, 8, 4096, 4112, 0, 1, 1, 0}, true);
   run({"swin      B1 H8 N32768 mode1", 1, 8, 32768, 32768, 1, 0, 0, 4096}, true);
   return g_fail ? 1 : 0;

@@ -358,6 +358,56 @@ static void run_vt(const char* name, int M, int N, int K, int split, int rows_pe
   report((nm + " [v^T]").c_str(), to_float(dvt.p, expvt.size(), RFB_BF16), expvt, 2e-2, 1.2e-2, (int)vt_ld);
 }
 
+// The residual-stream epilogue must not depend on the tile width: the row-sharded scene stage runs few-row
+// launches on 128-wide tiles and has to reproduce the single-GPU schedule (256-wide tiles) bit for bit.
+static void run_resid_widths(const char* name, int M, int N, int K, bool maps) {
+  std::vector<uint16_t> hA = rand16((size_t)M * K, 25, 1.0f, RFB_BF16), hW = rand16((size_t)N * K, 26, 0.05f, RFB_BF16);
+  DevBuf<uint16_t> dA((size_t)M * K), dW((size_t)N * K);
+  dA.up(hA), dW.up(hW);
+  std::vector<float> hres = rand32((size_t)M * N, 27, 1.0f), hparts((size_t)M * 8);
+  for (size_t i = 0; i < hparts.size(); ++i) hparts[i] = 20.f + 100.f * (0.5f + 0.5f * hval(28, (int)i));
+  std::vector<int> hmap(M), hrmap(M);
+  for (int m = 0; m < M; ++m) hmap[m] = (m * 5 + 3) % M, hrmap[m] = (m * 3 + 1) % M;
+  DevBuf<float> dparts(hparts.size());
+  dparts.up(hparts);
+  DevBuf<int> dmap(M), drmap(M);
+  dmap.up(hmap), drmap.up(hrmap);
+  std::vector<float> out[2], sq[2];
+  std::vector<uint16_t> o16[2];
+  for (int w = 0; w < 2; ++w) {
+    DevBuf<float> dx((size_t)M * N), dsq((size_t)M * (N / 128));
+    DevBuf<uint16_t> d16((size_t)M * N);
+    dx.up(hres), dsq.fill_byte(0x7f), d16.fill_byte(0);
+    rfb_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.M = M, a.N = N, a.K = K, a.A = dA.p, a.lda = K, a.W = dW.p, a.ldw = K, a.dtype = RFB_BF16, a.epi = RFB_EPI_STORE;
+    a.in_sumsq = dparts.p, a.in_sumsq_ld = 8, a.in_sumsq_parts = 8, a.norm_dim = 1024, a.norm_eps = 1e-6f;
+    a.out = dx.p, a.out_dtype = RFB_F32, a.ldo = N, a.res1 = dx.p, a.res_dtype = RFB_F32, a.ldres = N;
+    a.out_sumsq = dsq.p, a.out_sumsq_ld = N / 128, a.out16 = d16.p, a.out16_dtype = g_o16, a.ld16 = N;
+    if (maps) a.row_map = drmap.p, a.aux_row_map = dmap.p;
+    a.bn_override = w == 0 ? 256 : 128;
+    int rc = rfb_gemm(&a, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc != RFB_OK || e != cudaSuccess) {
+      printf("[FAIL] %-46s bn=%d rc=%d cuda=%s\n", name, a.bn_override, rc, cudaGetErrorString(e));
+      g_fail++;
+      if (e != cudaSuccess) exit(3);
+      return;
+    }
+    out[w] = dx.down(), sq[w] = dsq.down();
+    o16[w].resize((size_t)M * N);
+    CK(cudaMemcpy(o16[w].data(), d16.p, o16[w].size() * 2, cudaMemcpyDeviceToHost));
+  }
+  const bool same = !memcmp(out[0].data(), out[1].data(), out[0].size() * 4) &&
+                    !memcmp(sq[0].data(), sq[1].data(), sq[0].size() * 4) &&
+                    !memcmp(o16[0].data(), o16[1].data(), o16[0].size() * 2);
+  size_t nsq = 0;
+  for (size_t i = 0; i < sq[0].size(); ++i) nsq += memcmp(&sq[0][i], &sq[1][i], 4) != 0;
+  printf("[%s] %-46s 256- vs 128-wide tiles: %s (%zu of %zu partial sums differ)\n", same ? " ok " : "FAIL", name,
+         same ? "bit-identical" : "DIFFERENT", nsq, sq[0].size());
+  if (!same) g_fail++;
+}
+
 // micro-benchmark of the fused residual / projection epilogues at the decoder's shapes
 static void bench_fused(const char* name, int M, int N, int K, bool res, bool sumsq, bool o16, bool in_sq, bool maps,
                         bool f32out) {
@@ -496,6 +546,9 @@ int main(int argc, char** argv) {
       run_fused("EK_RESID 1031x1024x512 res", 1031, 1024, 512, 0, false, false, true, false, 1);
       run_fused("EK_RESID 1031x512x256 res rowmap auxmap", 1031, 512, 256, 0, false, true, true, true, 1);
       run_fused("EK_PROJ16 1031x2048x256", 1031, 2048, 256, 0, false, false, false, false, 2);
+      run_fused("EK_RESID narrow tile 130x1024x512 res", 130, 1024, 512, 0, false, false, true, false, 1);
+      run_resid_widths("EK_RESID 520x1024x1024", 520, 1024, 1024, false);
+      run_resid_widths("EK_RESID 1031x512x256 rowmap auxmap", 1031, 512, 256, true);
       run_vt("fused qkv (generic) 517x768x256 split 512", 517, 768, 256, 512, 0, false);
       run_vt("fused qkv (generic) 2x264 rows, batched v^T", 528, 768, 256, 512, 264, false);
       run_vt("fused qkv (PROJ16) 1031x1536x256 split 1024", 1031, 1536, 256, 1024, 0, true);
@@ -514,6 +567,13 @@ int main(int argc, char** argv) {
       bench("dec 8v w2+res  ", 32768, 1024, 4096, RFB_EPI_STORE, RFB_F32, bn);
       bench("dec 8v q_proj  ", 32768, 1024, 1024, RFB_EPI_STORE, RFB_F32, bn);
       bench("square 8192    ", 8192, 8192, 8192, RFB_EPI_STORE, RFB_BF16, bn);
+    }
+    bench_fused("shard/8 wo: res+sumsq+out16 ", 520, 1024, 1024, true, true, true, false, false, true);
+    bench_fused("shard/8 w2: res+sumsq+out16 ", 520, 1024, 4096, true, true, true, false, false, true);
+    for (int bn : {256, 128, 64, 0}) {
+      bench("shard/8 tokens K=13312", 504, 1024, 13312, RFB_EPI_STORE, RFB_BF16, bn);
+      bench("shard/8 w13 swiglu    ", 520, 8192, 1024, RFB_EPI_SWIGLU, RFB_BF16, bn);
+      bench("shard/8 qk f32        ", 520, 2048, 1024, RFB_EPI_STORE, RFB_BF16, bn);
     }
     bench_fused("dec wout: res+sumsq+out16 ", 16384, 1024, 1024, true, true, true, false, false, true);
     bench_fused("dec s.wo: res+sumsq+out16+map", 16384, 1024, 1024, true, true, true, false, true, true);

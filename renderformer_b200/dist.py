@@ -17,6 +17,9 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -47,12 +50,96 @@ def all_gather_rows(full: torch.Tensor, chunk: torch.Tensor, group=None) -> None
         dist.all_gather([full[r * s:(r + 1) * s] for r in range(world)], chunk.clone(), group=group)
 
 
+class SymmKVStore:
+    """Peer-mapped [k | v] row store of the row-sharded scene stage: two buffers [rows, width] (16 bit) in
+    symmetric memory (`torch.distributed._symmetric_memory`: the same allocation on every rank, every rank's copy
+    mapped into every other rank's address space over NVLink, plus -- where the NVSwitch supports NVLS -- ONE
+    multicast address that aliases all of them).  `rfb_qkv_post` stores a rank's rows through `dst(i)`; `barrier()`
+    is a signal-pad rendezvous of all ranks on the current stream (capturable in a CUDA graph), after which every
+    rank may read `buf(i)`.  This replaces the per-layer NCCL all-gather (the collective is fused into the kernel
+    that produces the rows: a rank's stores ARE the transfer)."""
+
+    def __init__(self, group, rows: int, width: int, dtype, device, multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass  # newer torch: not needed (deprecated)
+        self.t = symm_mem.empty((2, rows, width), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.t, pg)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        off = self.t.data_ptr() - int(self.hdl.buffer_ptrs[self.rank])  # the tensor's offset inside the mapped block
+        self._buf_bytes = rows * width * self.t.element_size()
+        self._peers = [int(ptr) + off for ptr in self.hdl.buffer_ptrs]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self._mc = mc + off if (multicast and mc) else 0
+        self.t.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    @property
+    def multicast(self) -> bool:
+        return self._mc != 0
+
+    def buf(self, i: int) -> torch.Tensor:
+        return self.t[i]
+
+    def dst(self, i: int):
+        """(device addresses to store buffer i's rows to, multicast flag)."""
+        if self._mc:
+            return [self._mc + i * self._buf_bytes], True
+        return [ptr + i * self._buf_bytes for ptr in self._peers], False
+
+    def barrier(self) -> None:
+        self.hdl.barrier(channel=0)
+
+
+_KV_STORES = {}
+_KV_PUSH_BROKEN = [False]
+
+
+def _kv_store_factory(group):
+    """kv_store callable for RowShard, or None (RFB_KV_PUSH=0, CPU / gloo groups, more than 8 ranks, or symmetric
+    memory that cannot be set up here -- all ranks then agree to keep the NCCL all-gather).  RFB_KV_PUSH=1 keeps
+    the peer-mapped stores but does without the multicast address (one plain store per peer)."""
+    mode = os.environ.get("RFB_KV_PUSH", "2")
+    world, _ = _world()
+    if mode == "0" or not torch.cuda.is_available() or dist.get_backend(group) != "nccl" or world > 8:
+        return None
+
+    def factory(rows, width, dtype, device):
+        if _KV_PUSH_BROKEN[0]:
+            return None
+        key = (id(group), rows, width, dtype, str(device), mode)
+        st = _KV_STORES.get(key)
+        if st is None:
+            err = None
+            try:
+                st = SymmKVStore(group, rows, width, dtype, device, multicast=(mode != "1"))
+            except Exception as e:  # noqa: BLE001 -- any set-up failure: agree on the fallback below
+                err, st = e, None
+            ok = torch.tensor([0 if st is None else 1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0:
+                _KV_PUSH_BROKEN[0] = True
+                if dist.get_rank(group) == 0:
+                    print(f"renderformer_b200.dist: symmetric-memory k|v store unavailable ({err!r}); "
+                          "falling back to the NCCL all-gather", file=sys.stderr, flush=True)
+                return None
+            if len(_KV_STORES) >= 4:
+                _KV_STORES.pop(next(iter(_KV_STORES)))
+            _KV_STORES[key] = st
+        return st
+    return factory
+
+
 def row_shard(group=None) -> Optional[RowShard]:
     """RowShard of the current process group (None when there is one rank)."""
     world, rank = _world()
     if world == 1:
         return None
-    return RowShard(rank, world, lambda full, chunk: all_gather_rows(full, chunk, group))
+    return RowShard(rank, world, lambda full, chunk: all_gather_rows(full, chunk, group), _kv_store_factory(group))
 
 
 def broadcast_scene_state(state: SceneState, src: int = 0) -> SceneState:

@@ -78,6 +78,11 @@ class RowShard:
     rank: int
     world: int
     all_gather: Callable[[torch.Tensor, torch.Tensor], None]
+    # optional (renderformer_b200.dist.SymmKVStore): kv_store(rows, width, dtype, device) -> peer-mapped, double-
+    # buffered [k | v] row store.  With it the per-layer all-gather disappears: the kernel that produces a rank's
+    # k | v rows stores them straight into every rank's memory (NVLS multicast or peer stores over NVLink,
+    # rfb_qkv_post) and the ranks meet at a signal-pad barrier before the attention reads them.
+    kv_store: Optional[Callable] = None
 
     def shard_rows(self, ntp: int) -> int:
         return _rup(-(-ntp // self.world), 8)
@@ -354,6 +359,16 @@ class Engine:
         return SceneState(B, N, Nt, Ntp, x.view(B, Ntp, self.cfg.latent_dim), tri, mask_u8, bits, k_all, v_all,
                           self.cfg.view_transformer_latent_dim)
 
+    @staticmethod
+    def enc_kv_split_tiles(Ntp: int) -> int:
+        """Key-chunk length (in 128-key tiles) of the encoder's self-attention; 0 = no split.  Chunks of about 11
+        tiles, at most 4: the chunks run on separate CTAs, which is what keeps the SMs busy when a rank of the
+        row-sharded schedule holds a few hundred query rows.  A function of the key count ONLY, so that every
+        schedule (one GPU or N ranks) does the same arithmetic per row."""
+        n_tiles = (Ntp + 127) // 128
+        splits = max(1, min(4, n_tiles // 11))
+        return 0 if splits == 1 else -(-n_tiles // splits)
+
     def encoder_layers(self, x, pos, bits, words, B, Ntp, taps=None):
         """TransformerEncoder.forward (layers/attention.py:579-590) on x fp32 [B*Ntp, d] (updated in place),
         pos [B, Ntp, 9], packed key mask `bits` [B, words].  State carried between GEMMs: x (fp32 residual),
@@ -370,6 +385,8 @@ class Engine:
         ops.rowstat(x, xb, xsq, rows=rows, d=d)
         if taps is not None:  # per-layer (16-bit stream, row sums) snapshots: what the sharded schedule all-gathers
             taps.setdefault("enc_stream", []).append((xb.clone(), xsq.clone()))
+        kst = self.enc_kv_split_tiles(Ntp)
+        ws = self._e((max(ops.attention_ws_elems(B, H, Ntp, Ntp, kst), 1),), f32) if kst else None
         for i in range(cfg.num_layers):
             o = f"enc{i}."
             vt = self._e((B, d, Ntp), bf)
@@ -382,7 +399,7 @@ class Engine:
             att = self._e((rows, d), bf)
             ops.attention(qkr, qkr[:, d:], vt, att, B=B, H=H, Nq=Ntp, Nk=Ntp, ldq=2 * d, ldk=2 * d, ldvt=Ntp, ldo=d,
                           q_bs=Ntp * 2 * d, k_bs=Ntp * 2 * d, vt_bs=d * Ntp, o_bs=Ntp * d, mask_bits=bits,
-                          mask_bs=words)
+                          mask_bs=words, kv_split_tiles=kst, split_ws=ws)
             ops.gemm(att, w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2)
             g = ops.gemm(xb2, w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2, **nrm)
             ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb)
@@ -491,34 +508,38 @@ class Engine:
 
         # ---- per layer every rank projects, normalises and rotates ITS rows, then ONE all-gather moves the 16-bit
         # [k | v] rows of all ranks (row r of `kv` = [d k | d v]); V is transposed locally for the attention kernel
-        S_ = S
-        kv = self._e((sh.world * S_, 2 * d), bf)
-        kv_chunk = kv[sh.rank * S_:(sh.rank + 1) * S_]
+        store = sh.kv_store(sh.world * S, 2 * d, bf, dev) if sh.kv_store is not None else None
+        kv_local = None if store is not None else self._e((sh.world * S, 2 * d), bf)
         nrm = dict(norm_dim=d, norm_eps=EPS)
         n_own = max(rows, 1)
         xb, xsq = self._e((n_own, d), bf), self._e((n_own, P), f32)
         xb2, xsq2 = self._e((n_own, d), bf), self._e((n_own, P), f32)
-        qk32 = self._e((n_own, 2 * d), f32)
+        qkv32 = self._e((n_own, 3 * d), f32)
         qr = self._e((n_own, d), bf)
         att = self._e((n_own, d), bf)
         vt = self._e((1, d, Ntp), bf)
+        kst = self.enc_kv_split_tiles(Ntp)
+        ws = self._e((max(ops.attention_ws_elems(1, H, n_own, Ntp, kst), 1),), f32) if kst else None
         if rows > 0:
             ops.rowstat(x, xb, xsq, rows=rows, d=d)
         for i in range(cfg.num_layers):
             o = f"enc{i}."
-            wqkv = w[o + "wqkv"]
+            # the k | v rows of layer i live in buffer i & 1 of the store: a fast rank may already push layer i + 1
+            # while a slow one still attends layer i (it cannot be further ahead: one barrier per layer)
+            kv = store.buf(i & 1) if store is not None else kv_local
+            dsts, mc = store.dst(i & 1) if store is not None else ([kv.data_ptr()], False)
             if rows > 0:
-                ops.gemm(xb[:rows], wqkv[:2 * d], out=qk32, in_sumsq=xsq[:rows], **nrm)                 # q | k, fp32
-                ops.gemm(xb[:rows], wqkv[2 * d:], out=kv[r0:r1, d:], in_sumsq=xsq[:rows], **nrm)       # v -> 16 bit
-                ops.qknorm_rope(qk32, w[o + "qkn"][:d], qr, rows=rows, d=d, nseg=1, ldx=2 * d, ldo=d, pos=pos[r0:r1],
-                                freqs=w["enc.freqs"], eps=EPS)
-                ops.qknorm_rope(qk32[:, d:], w[o + "qkn"][d:], kv[r0:r1], rows=rows, d=d, nseg=1, ldx=2 * d, ldo=2 * d,
-                                pos=pos[r0:r1], freqs=w["enc.freqs"], eps=EPS)
-            sh.all_gather(kv, kv_chunk)
+                ops.gemm(xb[:rows], w[o + "wqkv"], out=qkv32, in_sumsq=xsq[:rows], **nrm)               # [q | k | v], fp32
+                ops.qkv_post(qkv32, w[o + "qkn"], qr, dsts, multicast=mc, ldkv=2 * d, row0=r0, rows=rows, d=d,
+                             pos=pos[r0:r1], freqs=w["enc.freqs"], eps=EPS)
+            if store is not None:
+                store.barrier()
+            else:
+                sh.all_gather(kv, kv[sh.rank * S:(sh.rank + 1) * S])
             ops.transpose16(kv[:Ntp, d:], vt[0], rows=Ntp, cols=d)
             if rows > 0:
                 ops.attention(qr, kv, vt, att, B=1, H=H, Nq=rows, Nk=Ntp, ldq=d, ldk=2 * d, ldvt=Ntp, ldo=d,
-                              mask_bits=bits, mask_bs=words)
+                              mask_bits=bits, mask_bs=words, kv_split_tiles=kst, split_ws=ws)
                 ops.gemm(att[:rows], w[o + "wo"], out=x, res1=x, out_sumsq=xsq2, out16=xb2, M=rows)
                 g = ops.gemm(xb2[:rows], w[o + "w13"], epi=L.EPI_SWIGLU, out_dtype=bf, in_sumsq=xsq2[:rows], **nrm)
                 ops.gemm(g, w[o + "w2"], out=x, res1=x, out_sumsq=xsq, out16=xb, M=rows)

@@ -62,12 +62,13 @@ class AttnArgs(C.Structure):
         ("norm_dim", C.c_int),
         ("norm_eps", C.c_float),
         ("dtype", C.c_int),
+        ("kv_split_tiles", C.c_int), ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_longlong),
     ]
 
 
 # every symbol include/rfb200.h declares (tests/test_abi.py checks the built library exports them)
 SYMBOLS = [
-    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope", "rfb_qknorm_rope_table",
+    "rfb_version", "rfb_launch_count", "rfb_gemm", "rfb_attention", "rfb_attention_ws_bytes", "rfb_rmsnorm", "rfb_rowstat", "rfb_qknorm_rope", "rfb_qknorm_rope_table", "rfb_qkv_post",
     "rfb_token_assemble", "rfb_texture_prep", "rfb_texture_const_prep", "rfb_vn_encode", "rfb_ray_tokens", "rfb_ray_map_tokens", "rfb_ray_map", "rfb_positions",
     "rfb_pack_mask", "rfb_cast", "rfb_transpose16", "rfb_pixel_shuffle", "rfb_im2col_s2", "rfb_upsample_bilinear", "rfb_ldr_quantize",
 ]
@@ -94,6 +95,7 @@ def load() -> C.CDLL:
         "rfb_rowstat": [p, p, i, ll, p, i, i, i, i, p, p],
         "rfb_qknorm_rope_table": [p, ll, p, p, i, ll, i, i, i, f, p, p, ll, p],
         "rfb_qknorm_rope": [p, ll, i, p, p, i, ll, i, i, i, f, p, p, i, p],
+        "rfb_qkv_post": [p, ll, p, p, ll, C.POINTER(C.c_void_p), i, i, ll, ll, i, i, f, p, p, i, i, p],
         "rfb_token_assemble": [p, p, p, p, p, p, i, p, i, i, i, i, p],
         "rfb_texture_prep": [p, p, ll, i, i, i, p],
         "rfb_texture_const_prep": [p, p, ll, i, i, i, p],
@@ -114,6 +116,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = i
+    lib.rfb_attention_ws_bytes.argtypes = [i, i, i, i, i]
+    lib.rfb_attention_ws_bytes.restype = ll
     _lib = lib
     return lib
 

@@ -142,10 +142,18 @@ def _rup8(n: int) -> int:
 
 def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0, vt_bs=0, o_bs=0,
               mask_bits=None, mask_bs=0, mode=0, group_id=None, group_period=0, scale=None,
-              q_sumsq=None, k_sumsq=None, sumsq_ld=1, sumsq_parts=1, norm_dim=0, norm_eps=1e-6):
+              q_sumsq=None, k_sumsq=None, sumsq_ld=1, sumsq_parts=1, norm_dim=0, norm_eps=1e-6,
+              kv_split_tiles=0, split_ws=None):
+    """`kv_split_tiles` > 0 (mode 0): key chunks of that many 128-key tiles on separate CTAs + an ordered merge;
+    `split_ws` = float32 scratch of at least `attention_ws_elems(...)` elements."""
     _need_cuda(Q, K, Vt, O)
     lib = L.load()
     a = L.AttnArgs()
+    if kv_split_tiles > 0 and attention_ws_elems(B, H, Nq, Nk, kv_split_tiles) > 0:
+        if split_ws is None or split_ws.dtype != torch.float32 or not split_ws.is_contiguous():
+            raise L.RfbError("key-split attention needs a contiguous float32 scratch tensor (split_ws)")
+        _need_cuda(split_ws)
+        a.kv_split_tiles, a.split_ws, a.split_ws_bytes = kv_split_tiles, split_ws.data_ptr(), split_ws.numel() * 4
     a.B, a.H, a.Nq, a.Nk = B, H, Nq, Nk
     a.Q, a.ldq, a.q_batch_stride = Q.data_ptr(), ldq, q_bs
     a.K, a.ldk, a.k_batch_stride = K.data_ptr(), ldk, k_bs
@@ -163,6 +171,25 @@ def attention(Q, K, Vt, O, *, B, H, Nq, Nk, ldq, ldk, ldvt, ldo, q_bs=0, k_bs=0,
     L.check(_timed("attention", 4.0 * B * H * Nq * keys * 128, lambda: lib.rfb_attention(C.byref(a), _stream()),
                    f"B={B} H={H} Nq={Nq} Nk={Nk} mode={mode}"), "rfb_attention")
     return O
+
+
+def qkv_post(x, w_qk, out_q, kv_ptrs, *, multicast=False, ldkv, row0, rows, d, pos=None, freqs=None, eps=1e-6):
+    """Fused [q | k | v] post-processing + all-gather of the row-sharded scene stage (rfb_qkv_post): x fp32
+    [rows, 3d]; q -> out_q; k | v -> row row0 + r of every [k | v] row store in `kv_ptrs` (device addresses: own
+    store + peer-mapped stores, or one NVLS multicast address with `multicast`)."""
+    _need_cuda(x, w_qk, out_q)
+    nf = 0 if freqs is None else freqs.numel()
+    arr = (C.c_void_p * len(kv_ptrs))(*[int(p) for p in kv_ptrs])
+    L.check(_timed("qkv_post", 0.0, lambda: L.load().rfb_qkv_post(
+        x.data_ptr(), x.stride(0), w_qk.data_ptr(), out_q.data_ptr(), out_q.stride(0), arr, len(kv_ptrs),
+        1 if multicast else 0, ldkv, row0, rows, d, eps, _p(pos), _p(freqs), nf, _DT[out_q.dtype], _stream()),
+        f"rows={rows} d={d} dst={len(kv_ptrs)} mc={int(bool(multicast))}"), "rfb_qkv_post")
+    return out_q
+
+
+def attention_ws_elems(B, H, Nq, Nk, kv_split_tiles) -> int:
+    """float32 elements of scratch a key-split attention call needs (0: the call does not split)."""
+    return int(L.load().rfb_attention_ws_bytes(B, H, Nq, Nk, kv_split_tiles)) // 4
 
 
 def rmsnorm(x, w, out, *, rows, d, eps=1e-6, gather=None, ldx=None, ldo=None):

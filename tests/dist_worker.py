@@ -65,6 +65,15 @@ def main():
         pipe.cuda_graphs = False
         del pipe, model
         torch.cuda.empty_cache()
+    from renderformer_b200 import dist as rdist
+    how = "nccl all-gather"
+    if rdist._KV_STORES:
+        how = "multicast stores" if next(iter(rdist._KV_STORES.values())).multicast else "peer stores"
+    if rank == 0:
+        print(f"k|v exchange of the row-sharded stage: {how} (RFB_KV_PUSH={os.environ.get('RFB_KV_PUSH', '2')})", flush=True)
+    if os.environ.get("RFB_KV_PUSH", "2") != "0" and not rdist._KV_STORES:
+        print(f"[rank {rank}] symmetric-memory store was requested but is not in use", flush=True)
+        ok = False
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     good = flag.item() == 1

@@ -35,13 +35,15 @@ def _pipe(cfg, seed, dev="cuda:0"):
     return pipe
 
 
+@pytest.mark.parametrize("use_store", [False, True], ids=["all-gather", "kv-store"])
 @pytest.mark.parametrize("cfg_name,n_tris,pad_to,world", [
     ("tiny_swin", 100, None, 2),
     ("tiny_swin", 37, 48, 4),          # ragged count, padding, more ranks than 128-row tiles
     ("tiny_swin", 5, None, 8),         # fewer rows than ranks x 8: trailing ranks own nothing
     ("v1_1_swin_large", 1000, 1024, 8),
+    ("v1_1_swin_large", 2900, None, 4),  # 23 key tiles: the key-split attention (2 chunks) in both schedules
 ])
-def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world):
+def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world, use_store):
     from renderformer_b200.engine import RowShard
     cfg = RenderFormerConfig.named(cfg_name)
     pipe = _pipe(cfg, 5)
@@ -81,7 +83,25 @@ def test_row_sharded_encoder_emulated(cfg_name, n_tris, pad_to, world):
                 f32[:ref.Ntp, d // 2:d // 2 + P].copy_(xsq_fin)
             step[0] += 1
 
-        sh = RowShard(rank, world, fake_all_gather)
+        class FakeStore:  # stands in for dist.SymmKVStore: the barrier "receives" the other ranks' rows
+            def __init__(self, rows, width, dtype, device):
+                self.t = torch.zeros((2, rows, width), dtype=dtype, device=device)
+
+            def buf(self, i):
+                return self.t[i]
+
+            def dst(self, i):
+                return [self.t[i].data_ptr()], False
+
+            def barrier(self):
+                fake_all_gather(self.t[step[0] & 1], None)
+
+        stores = {}
+
+        def kv_store(rows, width, dtype, device):
+            return stores.setdefault((rows, width, dtype), FakeStore(rows, width, dtype, device))
+
+        sh = RowShard(rank, world, fake_all_gather, kv_store if use_store else None)
         st = eng.encode_scene(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], shard=sh, gather_seq=True)
         assert step[0] == cfg.num_layers + 1 and st.complete
         for a, b, name in zip(st.tensors(), ref.tensors(), ("seq", "tri", "mask", "bits", "k_all", "v_all")):
@@ -102,12 +122,16 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_sharded_render_equals_single_gpu():
+@pytest.mark.parametrize("kv_push", ["2", "1", "0"], ids=["multicast-stores", "peer-stores", "nccl-all-gather"])
+def test_sharded_render_equals_single_gpu(kv_push):
+    """`kv_push` = RFB_KV_PUSH: how a layer's k | v rows reach the other ranks -- stores through the NVLS multicast
+    address fused into the producing kernel (default), plain stores into every peer's mapped memory, or the NCCL
+    all-gather."""
     n = 2  # two ranks exercise every code path; bench.py re-checks bit-identity at whatever N it runs on
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_worker.py")]
-    env = dict(os.environ, NCCL_DEBUG="WARN")
+    env = dict(os.environ, NCCL_DEBUG="WARN", RFB_KV_PUSH=kv_push)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
     tail = (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail
