@@ -1,6 +1,8 @@
 // Bandwidth-bound helpers of the DPT patch decoder (layers/dpt.py), NHWC fp16 activations:
 // ConvTranspose(k = s) pixel-shuffle scatter, im2col for the stride-2 3x3 conv, and bilinear
 // align_corners=True resampling.  All convolutions themselves run through rfb_gemm.
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "host_util.h"
@@ -101,6 +103,81 @@ __global__ void upsample_bilinear_kernel(const uint4* __restrict__ in, uint4* __
   }
 }
 
+// Tiled variant for ~2x magnification of 128-channel maps (every FeatureFusionBlock of the DPT head at the released
+// resolutions).  The kernel above fetches four 16-byte taps per 16 bytes written, all through L1/L2: it runs at the
+// L2 -> SM rate, four times the HBM traffic.  Here a block owns an 8 x 32 pixel output tile: the <= 6 x 18 input
+// pixels underneath are staged in shared memory once (coalesced 16-byte loads), a thread walks one (column,
+// 8-channel group) of the tile downwards keeping the horizontally interpolated input rows y0 / y0+1 in
+// registers (two shared-memory reads per NEW input row instead of four per output), and every warp store is
+// 512 contiguous bytes.  Arithmetic identical to the kernel above (same expressions, same rounding).
+constexpr int kUpTH = 8, kUpTW = 32, kUpRows = 6, kUpCols = 18, kUpC8 = 16;
+
+__global__ void __launch_bounds__(256)
+    upsample_bilinear_tiled_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int Hi, int Wi, int Ho, int Wo) {
+  __shared__ uint4 tile[kUpRows * kUpCols * kUpC8];  // 27 KB
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * kUpTH, X0 = blockIdx.x * kUpTW;
+  const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const int iy0 = min((int)(Y0 * sy), Hi - 1), ix0 = min((int)(X0 * sx), Wi - 1);
+  const int ylast = min(Y0 + kUpTH, Ho) - 1, xlast = min(X0 + kUpTW, Wo) - 1;
+  const int rows = min(min((int)(ylast * sy), Hi - 1) + 1, Hi - 1) - iy0 + 1;  // <= kUpRows (host-checked scale)
+  const int cols = min(min((int)(xlast * sx), Wi - 1) + 1, Wi - 1) - ix0 + 1;  // <= kUpCols
+  const uint4* src = in + (long long)b * Hi * Wi * kUpC8;
+  for (int i = threadIdx.x; i < rows * cols * kUpC8; i += 256) {
+    const int c = i % kUpC8, px = (i / kUpC8) % cols, py = i / (kUpC8 * cols);
+    tile[(py * kUpCols + px) * kUpC8 + c] = __ldg(src + ((long long)(iy0 + py) * Wi + ix0 + px) * kUpC8 + c);
+  }
+  __syncthreads();
+  uint4* dst = out + (long long)b * Ho * Wo * kUpC8;
+#pragma unroll 1
+  for (int u = threadIdx.x; u < kUpTW * kUpC8; u += 256) {  // (column, channel group) strips of the tile
+    const int c = u % kUpC8, xo = X0 + u / kUpC8;
+    if (xo >= Wo) continue;
+    const float fx = xo * sx;
+    const int x0 = min((int)fx, Wi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float wx = fx - x0;
+    auto hrow = [&](int y, float (&h)[8]) {  // horizontally interpolated input row y at this column
+      float a[8], bb[8];
+      h8_to_f(tile[((y - iy0) * kUpCols + (x0 - ix0)) * kUpC8 + c], a);
+      h8_to_f(tile[((y - iy0) * kUpCols + (x1 - ix0)) * kUpC8 + c], bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = a[i] + (bb[i] - a[i]) * wx;
+    };
+    float top[8], bot[8];
+    int ytop = -1, ybot = -1;
+    for (int yo = Y0; yo <= ylast; ++yo) {
+      const float fy = yo * sy;
+      const int y0 = min((int)fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
+      const float wy = fy - y0;
+      if (y0 != ytop) {
+        if (y0 == ybot) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) top[i] = bot[i];
+        } else {
+          hrow(y0, top);
+        }
+        ytop = y0;
+      }
+      if (y1 != ybot) {
+        if (y1 == ytop) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bot[i] = top[i];
+        } else {
+          hrow(y1, bot);
+        }
+        ybot = y1;
+      }
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = top[i] + (bot[i] - top[i]) * wy;
+      uint4 v;
+      v.x = pack_f16(o[0], o[1]), v.y = pack_f16(o[2], o[3]), v.z = pack_f16(o[4], o[5]), v.w = pack_f16(o[6], o[7]);
+      dst[((long long)yo * Wo + xo) * kUpC8 + c] = v;
+    }
+  }
+}
+
 static inline int grid_for(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = 148LL * 32;
@@ -173,6 +250,23 @@ extern "C" int rfb_im2col_s2(const void* in, void* out, int B, int H, int W, int
 extern "C" int rfb_upsample_bilinear(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                      rfb_stream_t stream) {
   if (!in || !out || C % 8) return RFB_ERR_ARG;
+  {
+    // tiled kernel: 128 channels, magnification >= ~1.9 in both directions (the tile's input footprint must fit)
+    static int tiled_on = -1;
+    if (tiled_on < 0) {
+      const char* e = getenv("RFB_UPSAMPLE_TILED");
+      tiled_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    const bool fits = (int)((kUpTH - 1) * sy) + 3 <= kUpRows && (int)((kUpTW - 1) * sx) + 3 <= kUpCols;
+    if (tiled_on && C == 8 * kUpC8 && fits && B <= 65535 && Ho >= kUpTH && Wo >= kUpTW) {
+      dim3 grid((Wo + kUpTW - 1) / kUpTW, (Ho + kUpTH - 1) / kUpTH, B);
+      upsample_bilinear_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, Hi, Wi, Ho, Wo);
+      g_launch_count++;
+      return check_launch("upsample_bilinear_tiled_kernel");
+    }
+  }
   const long long total = (long long)B * Ho * Wo * (C / 8);
   upsample_bilinear_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B,
                                                                               Hi, Wi, Ho, Wo, C / 8);

@@ -547,6 +547,11 @@ int main(int argc, char** argv) {
       run_fused("EK_RESID 1031x512x256 res rowmap auxmap", 1031, 512, 256, 0, false, true, true, true, 1);
       run_fused("EK_PROJ16 1031x2048x256", 1031, 2048, 256, 0, false, false, false, false, 2);
       run_fused("EK_RESID narrow tile 130x1024x512 res", 130, 1024, 512, 0, false, false, true, false, 1);
+      // more tiles than SMs: the cross-tile residual prefetch of the persistent epilogue
+      run_fused("EK_RESID 5000x1024x256 res (160 tiles)", 5000, 1024, 256, 0, false, false, true, false, 1);
+      run_fused("EK_RESID 4999x1024x128 res rowmap auxmap", 4999, 1024, 128, 0, false, true, true, true, 1);
+      run_resid_widths("EK_RESID 5000x1024x256 (160 / 320 tiles)", 5000, 1024, 256, false);
+      run_resid_widths("EK_RESID 4999x1024x128 rowmap auxmap", 4999, 1024, 128, true);
       run_resid_widths("EK_RESID 520x1024x1024", 520, 1024, 1024, false);
       run_resid_widths("EK_RESID 1031x512x256 rowmap auxmap", 1031, 512, 256, true);
       run_vt("fused qkv (generic) 517x768x256 split 512", 517, 768, 256, 512, 0, false);

@@ -275,3 +275,30 @@ def test_render_stream_sharded_single_rank():
     assert len(got) == len(want)
     for (sl, a), b, sc in zip(got, want, scenes):
         assert sl == slice(0, sc["c2w"].shape[1]) and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,Hi,Ho,C,tiled", [
+    (2, 32, 64, 128, True),      # FeatureFusionBlock 4 of the DPT head at 512^2 (tiled kernel)
+    (1, 128, 256, 128, True),
+    (1, 33, 66, 128, True),      # output not a multiple of the 8 x 32 tile
+    (3, 8, 16, 128, False),      # narrower than a tile: generic kernel
+    (1, 20, 37, 128, False),     # not ~2x: generic kernel
+    (1, 16, 32, 64, False),      # 64 channels: generic kernel
+])
+def test_upsample_bilinear_matches_interpolate(B, Hi, Ho, C, tiled):
+    """rfb_upsample_bilinear (both kernels) vs F.interpolate(mode='bilinear', align_corners=True) -- the
+    resize of FeatureFusionBlock.forward, layers/dpt.py:154-155 -- on NHWC fp16 maps."""
+    import torch.nn.functional as F
+    from renderformer_b200 import lib as L
+    from renderformer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((B, Hi, Hi, C), generator=g).to(torch.float16).cuda()
+    out = torch.zeros((B * Ho * Ho, C), dtype=torch.float16, device="cuda")
+    n0 = L.launch_count()
+    ops.upsample_bilinear(x.view(-1, C), out, B=B, Hi=Hi, Wi=Hi, Ho=Ho, Wo=Ho, C_=C)
+    torch.cuda.synchronize()
+    assert L.launch_count() == n0 + 1
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Ho), mode="bilinear", align_corners=True)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-3, f"max |d| {err:.3e}"   # fp16 output rounding of |x| < 4.5: half an ulp = 2e-3
