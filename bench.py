@@ -8,8 +8,10 @@
 
 One step = ONE JOB of fixed size: one scene through the view-independent stage and `--total-views`
 (32: BASELINE configs[2]) camera views of an orbit through the view-dependent stage, at any N
-("scaling": "strong").  At N > 1 the scene stage is row-sharded over the ranks (one NCCL all-gather per
-encoder layer), every rank renders total_views / N views, the images are gathered on rank 0.
+("scaling": "strong").  At N > 1 the scene stage is row-sharded over the ranks (per encoder layer every rank
+stores its k | v rows into all ranks' memories through the NVLS multicast address -- the exchange is fused into
+the producing kernel -- and the ranks meet at a signal-pad barrier; NCCL all-gather with RFB_KV_PUSH=0), every
+rank renders total_views / N views, the images are gathered on rank 0.
 `--views-per-gpu V` switches to the weak-scaling job (V views on every GPU).
 Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md §5).
 """
@@ -71,6 +73,17 @@ def load_peaks():
 
 def job_views(args, world):
     return args.views_per_gpu * world if args.views_per_gpu > 0 else args.total_views
+
+
+def kv_exchange_text() -> str:
+    """How the row-sharded scene stage moved a layer's k | v rows between the ranks in THIS run."""
+    from renderformer_b200 import dist as rdist
+    if rdist._KV_STORES:
+        mc = next(iter(rdist._KV_STORES.values())).multicast
+        how = "NVLS multicast stores" if mc else "peer-mapped NVLink stores"
+        return (f"per encoder layer every rank's k|v rows go to all ranks by {how} fused into the kernel that produces "
+                "them (rfb_qkv_post) + one signal-pad barrier; one NCCL all-gather of the final 16-bit stream")
+    return "one NCCL all-gather of the ranks' 16-bit k|v rows per encoder layer"
 
 
 def workload_text(args, world):
@@ -572,12 +585,12 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
                 "workload": workload_text(args, world),
-                "parallelism": (f"scene stage row-sharded over {world} ranks (one NCCL all-gather of the 16-bit residual stream per "
-                                f"encoder layer), {Vl} views per rank, image gather on rank 0" if world > 1 else "single GPU"),
+                "parallelism": (f"scene stage row-sharded over {world} ranks ({kv_exchange_text()}), "
+                                f"{Vl} views per rank, image gather on rank 0" if world > 1 else "single GPU"),
                 "views_per_decoder_pass": pipe.view_chunk,
                 "l2": "inputs + weights + activations (> 1.3 GB per step) exceed the 126 MB L2; no explicit flush",
-                "launch": ("one CUDA-graph replay per step and rank, NCCL all-gathers inside the graph; the image gather of "
-                           "job k is enqueued asynchronously and overlaps the scene stage of job k+1"
+                "launch": ("one CUDA-graph replay per step and rank, the ranks' k|v exchange and barriers inside the graph; "
+                           "the image gather of job k is enqueued asynchronously and overlaps the scene stage of job k+1"
                            if graphs else "eager launches from Python"),
                 "algorithmic_tflop_per_step": step_tflop,
                 "model_flops_utilisation": step_tflop / (ms_step * 1e-3) / world / load_peaks()[0],

@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tiles = p.split_tiles > 0 ? min(p.split_tiles, p.n_kv_tiles - j_begin) : p.n_kv_tiles;
+  // Short tail: when the LAST key tile of the sequence holds <= 32 keys (16 register tokens + a multiple of 128
+  // triangles is the common case) its products run 32 keys wide -- S = Q K^T with N = 32, P V with two K = 16 steps --
+  // and the softmax touches one 32-column chunk instead of four.  The skipped columns are masked keys, whose
+  // probabilities are exactly 0: the result is bit-identical to the full-width tile.
+  const int tail_local = (p.Nk - (p.n_kv_tiles - 1) * 128 <= 32) ? p.n_kv_tiles - 1 - j_begin : -1;  // local index or never
   const int kb = p.k_batched ? b : 0;
   const int vb = p.v_batched ? b : 0;
 
@@ -154,14 +159,16 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
     setmaxnreg_dec<kRegsWg0>();
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(F16 ? 0u : 1u, 128, 128);
+      const uint32_t idesc_tail = umma_idesc_f16(F16 ? 0u : 1u, 128, 32);
       auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T
         const int s = j % kStg;
         const uint64_t ad = umma_desc_sw128(smem_u32(sQ + t * kT2));
         const uint64_t bd = umma_desc_sw128(smem_u32(sK + s * kT2));
+        const uint32_t id = (j == tail_local) ? idesc_tail : idesc;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t off = (k >> 2) * (kH2 >> 4) + (k & 3) * 2;
-          umma_f16(tmem_base + t * 128, ad + off, bd + off, idesc, k != 0);
+          umma_f16(tmem_base + t * 128, ad + off, bd + off, id, k != 0);
         }
         umma_commit(&s_full[t]);
       };
@@ -170,10 +177,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
         mbar_wait(&p_full[t], j & 1);
         tc_fence_after();
         const uint64_t bd = umma_desc_sw128(smem_u32(sV + s * kT2));
+        const int ksteps = (j == tail_local) ? 2 : 8;  // short tail: 32 keys = two K = 16 steps
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t off = (k >> 2) * (kH2 >> 4) + (k & 3) * 2;
-          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, bd + off, idesc, (j | k) != 0);
+          if (k < ksteps)
+            umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, bd + off, idesc, (j | k) != 0);
         }
       };
       mbar_wait(q_full, 0);
@@ -240,27 +249,34 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
 
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      const int nc = (j == tail_local) ? 1 : 4;  // 32-column chunks of S that exist (short tail: one)
       uint32_t v[4][32];
       tmem_ld32(tS, v[0]);
-      tmem_ld32(tS + 32, v[1]);
-      tmem_ld32(tS + 64, v[2]);
-      tmem_ld32(tS + 96, v[3]);
+      if (nc == 4) {
+        tmem_ld32(tS + 32, v[1]);
+        tmem_ld32(tS + 64, v[2]);
+        tmem_ld32(tS + 96, v[3]);
+      }
       tmem_wait_ld();
 
       if (!all_valid) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint32_t bits = mw[c];
+          if (c < nc) {
+            const uint32_t bits = mw[c];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!((bits >> i) & 1u)) v[c][i] = 0xff800000u;  // -inf
+            for (int i = 0; i < 32; ++i)
+              if (!((bits >> i) & 1u)) v[c][i] = 0xff800000u;  // -inf
+          }
         }
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
+        if (c < nc) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+        }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -285,6 +301,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
       uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if (c >= nc) continue;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {

@@ -226,6 +226,13 @@ int main(int argc, char** argv) {
         {"swin mode1 B1 H8 N8192 period 4096", 1, 8, 8192, 8192, 1, 0, 0, 4096},
         {"fused q-norm B3 H2 Nq300 Nk400 shared KV", 3, 2, 300, 400, 0, 1, 1, 0, 1},
         {"fused q+k-norm swin mode1 B1 H2 N1024", 1, 2, 1024, 1024, 1, 0, 0, 256, 2},
+        // short tail (last key tile <= 32 keys runs 32 wide): 16 / 32 keys, 33 keys (full-width path), with masks and splits
+        {"short tail 16: random mask B3 H1 Nq200 Nk1040", 3, 1, 200, 1040, 0, 2, 0, 0},
+        {"short tail 32: prefix mask B2 H2 Nq300 Nk1056", 2, 2, 300, 1056, 0, 1, 0, 0},
+        {"tail 33 (full width) B2 H2 Nq300 Nk1057", 2, 2, 300, 1057, 0, 0, 0, 0},
+        {"short tail 1 key, no mask B1 H2 Nq130 Nk129", 1, 2, 130, 129, 0, 0, 0, 0},
+        {"short tail 16 + key split 3, random mask Nk1040", 3, 1, 200, 1040, 0, 2, 0, 0, 0, 3},
+        {"short tail alone in its chunk: split 4, Nk1040", 2, 2, 300, 1040, 0, 1, 0, 0, 0, 4},
         {"key split 2 B3 H1 Nq200 Nk1000 random mask", 3, 1, 200, 1000, 0, 2, 0, 0, 0, 2},
         {"key split 3 (3,3,2) B2 H2 Nq300 Nk1000 prefix", 2, 2, 300, 1000, 0, 1, 0, 0, 0, 3},
         {"key split 1: chunks with no valid key", 2, 2, 300, 600, 0, 3, 0, 0, 0, 1},
