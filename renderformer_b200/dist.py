@@ -3,11 +3,12 @@
 Both stages shard:
 
 * view-independent stage -- the token ROWS of the triangle sequence are split over the ranks
-  (`row_shard` -> engine.RowShard): every rank constructs, attends and feeds forward its own rows and
-  one all-gather per encoder layer exchanges the 16-bit copy of the residual stream (8.6 MB for 4096
-  triangles) that the next layer's K / V projection needs of all rows.  No rank waits for "the
-  encoder rank", no 300 MB K/V broadcast: the hoisted decoder K / V are recomputed from the gathered
-  stream on every rank (0.2 TFLOP).
+  (`row_shard` -> engine.RowShard): every rank constructs, projects, attends and feeds forward its own rows.
+  What a layer needs of the other ranks -- their 16-bit k | v rows (16.8 MB in total for 4096 triangles) -- is
+  written by the producing kernel itself into every rank's memory (`SymmKVStore`: symmetric memory, NVLS
+  multicast stores or peer stores over NVLink, then a signal-pad barrier); `RFB_KV_PUSH=0` keeps one NCCL
+  all-gather per layer instead.  No rank waits for "the encoder rank", no 300 MB K/V broadcast: the hoisted
+  decoder K / V are recomputed from the gathered final stream on every rank (0.2 TFLOP).
 * view-dependent stage -- every rank renders a contiguous slice of the views (`view_slice`); the
   only collective is the final image gather.
 

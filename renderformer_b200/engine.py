@@ -447,14 +447,16 @@ class Engine:
 
     def _encode_scene_sharded(self, triangles, texture, mask, vn, texture_is_log, sh: RowShard,
                               texture_own_rows: bool = False, gather_seq: bool = False) -> SceneState:
-        """One scene, token rows split over the ranks of `sh` (see RowShard).  Per layer and rank:
-        [q|k|v] projection, QK-norm and RoPE of the OWN rows, one all-gather of every rank's 16-bit [k | v]
-        rows (16.8 MB for 4096 triangles), a local transpose of V, attention of the own query rows against
-        all keys, out-projection + SwiGLU on the own rows.  Nothing is computed twice; after the last layer
-        one more gather collects the 16-bit stream + row sums that the hoisted decoder K / V are projected
-        from (replicated: 0.2 TFLOP is cheaper than moving the 300 MB result).  The arithmetic of a row does
-        not depend on which rank owns it: the result is bit-identical to the single-GPU schedule
-        (tests/test_dist_gpu.py)."""
+        """One scene, token rows split over the ranks of `sh` (see RowShard).  Per layer and rank: ONE fused
+        [q|k|v] projection of the OWN rows, `rfb_qkv_post` (QK-norm + RoPE of q and k, cast of v) which writes the
+        16-bit [k | v] rows into the layer's row store -- with `sh.kv_store` straight into EVERY rank's store (NVLS
+        multicast or peer stores: the all-gather is fused into the producer) followed by a barrier, otherwise into the
+        local buffer followed by one all-gather (16.8 MB for 4096 triangles) -- a local transpose of V, key-split
+        attention of the own query rows against all keys, out-projection + SwiGLU on the own rows.  Nothing is
+        computed twice; after the last layer one more gather collects the 16-bit stream + row sums that the hoisted
+        decoder K / V are projected from (replicated: 0.2 TFLOP is cheaper than moving the 300 MB result).  The
+        arithmetic of a row does not depend on which rank owns it or how many rows a launch holds: the result is
+        bit-identical to the single-GPU schedule (tests/test_dist_gpu.py)."""
         cfg, w, dev = self.cfg, self.w, self.device
         N = triangles.shape[1]
         d, H, dv = cfg.latent_dim, cfg.num_heads, cfg.view_transformer_latent_dim
