@@ -80,3 +80,17 @@ def test_dropin_import_surface_and_checkpoint_roundtrip(tmp_path):
     for k, v in pipe.model.state_dict().items():
         assert torch.equal(v, sd[k]), k
     assert pipe.to(torch.device("cpu")) is None and pipe.device.type == "cpu"
+
+
+def test_encoder_key_split_rule():
+    """Engine.enc_kv_split_tiles: chunk length of the key-split encoder attention.  It must be a function of the key
+    count only (every schedule -- one GPU or N ranks -- has to do the same arithmetic per row), give at most 4
+    chunks (rfb_attention accepts 8) and leave short sequences alone."""
+    from renderformer_b200.engine import Engine
+    for ntp in (8, 136, 1040, 2688):            # up to 21 key tiles: no split
+        assert Engine.enc_kv_split_tiles(ntp) == 0
+    for ntp, chunks in ((2920, 2), (4112, 3), (5648, 4), (8208, 4), (16400, 4)):
+        kst = Engine.enc_kv_split_tiles(ntp)
+        n_tiles = (ntp + 127) // 128
+        assert kst > 0 and -(-n_tiles // kst) == chunks, (ntp, kst)
+        assert kst * chunks >= n_tiles and kst * (chunks - 1) < n_tiles   # every chunk holds at least one tile
