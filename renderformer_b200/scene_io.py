@@ -253,8 +253,15 @@ def to_pipeline_inputs(scene: Dict[str, np.ndarray], pad_to: Optional[int] = Non
     vn = np.zeros((total, 3, 3), np.float32)
     tex13 = np.zeros((total, 13), np.float32)
     mask = np.zeros((total,), bool)
-    tri[:n], vn[:n], tex13[:n], mask[:n] = scene["triangles"], scene["vn"], scene["tex13"], True
-    tex = tex13 if constant_texture else expand_texture(tex13)
+    tri[:n], vn[:n], mask[:n] = scene["triangles"], scene["vn"], True
+    if "tex13" in scene:
+        tex13[:n] = scene["tex13"]
+        tex = tex13 if constant_texture else expand_texture(tex13)
+    else:  # a stored texel grid (load_h5): arbitrary textures, no constant-texture shortcut
+        if constant_texture:
+            raise ValueError("constant_texture needs per-triangle constants ('tex13'); this scene stores a texel grid")
+        tex = np.zeros((total,) + tuple(scene["texture"].shape[1:]), np.float32)
+        tex[:n] = scene["texture"]
     return {
         "triangles": torch.from_numpy(tri)[None], "texture": torch.from_numpy(tex)[None],
         "mask": torch.from_numpy(mask)[None], "vn": torch.from_numpy(vn)[None],
@@ -269,3 +276,32 @@ def save_npz(scene: Dict[str, np.ndarray], path: str) -> None:
 def load_npz(path: str) -> Dict[str, np.ndarray]:
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
+
+
+def load_h5(path: str) -> Dict[str, np.ndarray]:
+    """A scene file written by the reference's converter (scene_processor/to_h5.py:68-92; what
+    batch_infer.py:27-35 / infer.py:66-73 read): 'triangles' [N,3,3], 'texture' [N,13,32,32] (fp16 in the file),
+    'vn' [N,3,3], 'c2w' [V,4,4], 'fov' [V].  Needs the optional h5py package (not in this image: the numpy-only
+    route is tools/convert_scene.py -> .npz); the texel grid is kept as stored, so `to_pipeline_inputs` passes
+    it through instead of expanding per-triangle constants."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError(f"{path}: reading HDF5 scenes needs h5py; convert the scene JSON with "
+                          "tools/convert_scene.py (numpy only) instead") from e
+    with h5py.File(path, "r") as f:
+        return {"triangles": np.array(f["triangles"]).astype(np.float32), "texture": np.array(f["texture"]).astype(np.float32),
+                "vn": np.array(f["vn"]).astype(np.float32), "c2w": np.array(f["c2w"]).astype(np.float32),
+                "fov": np.array(f["fov"]).astype(np.float32).reshape(-1)}
+
+
+def load_scene_file(path: str) -> Dict[str, np.ndarray]:
+    """.npz (tools/convert_scene.py), .h5 / .hdf5 (the reference's converter) or .json (scene description)."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npz":
+        return load_npz(path)
+    if ext in (".h5", ".hdf5"):
+        return load_h5(path)
+    if ext == ".json":
+        return load_scene(path)
+    raise ValueError(f"{path}: unknown scene file type")

@@ -152,3 +152,43 @@ def test_cbox_fixture(golden_dir):
         again = sio.load_scene("/root/reference/examples/cbox.json")
         for k in s:
             np.testing.assert_array_equal(again[k], s[k])
+
+
+def test_scene_file_loader_dispatch(tmp_path, monkeypatch):
+    """.npz / .json go through the numpy-only route; .h5 (the reference converter's files, to_h5.py:68-92) needs
+    h5py and says so; with an h5py present the stored texel grid is passed through unexpanded."""
+    import sys
+    import types
+    sc = {"triangles": np.random.rand(5, 3, 3).astype(np.float32), "vn": np.random.rand(5, 3, 3).astype(np.float32),
+          "tex13": np.random.rand(5, 13).astype(np.float32), "c2w": np.eye(4, dtype=np.float32)[None], "fov": np.array([37.5], np.float32)}
+    p = str(tmp_path / "s.npz")
+    sio.save_npz(sc, p)
+    back = sio.load_scene_file(p)
+    assert all(np.array_equal(back[k], sc[k]) for k in sc)
+    with pytest.raises(ValueError):
+        sio.load_scene_file(str(tmp_path / "s.txt"))
+    monkeypatch.setitem(sys.modules, "h5py", None)  # import h5py -> ImportError
+    with pytest.raises(ImportError, match="convert_scene"):
+        sio.load_scene_file(str(tmp_path / "s.h5"))
+    grid = sio.expand_texture(sc["tex13"]).astype(np.float16)
+    stored = {"triangles": sc["triangles"], "texture": grid, "vn": sc["vn"], "c2w": sc["c2w"], "fov": sc["fov"]}
+
+    class File(dict):
+        def __init__(self, path, mode="r"):
+            super().__init__(stored)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+    h5 = types.ModuleType("h5py")
+    h5.File = File
+    monkeypatch.setitem(sys.modules, "h5py", h5)
+    got = sio.load_scene_file(str(tmp_path / "s.h5"))
+    assert got["texture"].dtype == np.float32 and got["fov"].shape == (1,)
+    inp = sio.to_pipeline_inputs(got, pad_to=8)
+    assert tuple(inp["texture"].shape) == (1, 8, 13, 32, 32) and inp["mask"][0].tolist() == [True] * 5 + [False] * 3
+    assert np.array_equal(inp["texture"][0, :5].numpy(), grid.astype(np.float32)) and not inp["texture"][0, 5:].any()
+    with pytest.raises(ValueError, match="constant_texture"):
+        sio.to_pipeline_inputs(got, constant_texture=True)
