@@ -71,3 +71,19 @@ def test_product_does_not_import_oracle():
                     with open(os.path.join(dirpath, fn)) as f:
                         src = f.read()
                     assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, fn)
+
+
+def test_integration_doc_binding_matches_the_library_struct():
+    """INTEGRATION.md shows the ctypes struct a maintainer would write on the reference side: it has to stay the
+    field-for-field mirror of rfb_gemm_args (same names, same order, same widths) as the header evolves."""
+    import ctypes
+    import re
+    from renderformer_b200 import lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = doc[doc.index("class GemmArgs"):doc.index("def linear_bf16")]
+    shown = re.findall(r'\("(\w+)", ctypes\.(\w+)\)', block)
+    real = [(n, t) for n, t in lib.GemmArgs._fields_]
+    assert [n for n, _ in shown] == [n for n, _ in real]
+    for (n, tname), (_, t) in zip(shown, real):
+        assert ctypes.sizeof(getattr(ctypes, tname)) == ctypes.sizeof(t), n
