@@ -411,27 +411,62 @@ class FrameWriter:
 
 def render_to_files(pipeline, scenes: Iterable[dict], names: Sequence[str], out_dir: str, resolution: int = 512,
                     torch_dtype=None, tone_mapper: str = "none", pad_to: Optional[int] = None,
-                    save_video: bool = False, workers: int = 4, fps: int = 24) -> List[str]:
+                    save_video: bool = False, workers: int = 4, fps: int = 24, sharded: bool = False) -> List[str]:
     """The batch_infer.py loop (batch_infer.py:122-172) with nothing serialised behind the renderer: `scenes`
     (host tensors, the keys of `render`) go through `pipeline.render_stream` (upload of scene i+1 and download
     of image i-1 overlap the kernels of scene i) and every frame is handed to a `FrameWriter`.  Files are
     named like the reference's: `{name}_view_{v}.exr`, `{name}_view_{v}.png`, `video.mp4`.  `names[i]` belongs
     to the i-th scene (a scene dict holding B > 1 scenes takes B consecutive names).  Returns the frame paths
-    (without extension) in order."""
+    (without extension) this process wrote, in order.
+
+    `sharded=True` (one process per GPU, `torch.distributed` initialised): every rank iterates the SAME scenes
+    through `dist.render_stream_sharded` -- scene stage row-sharded, each rank renders and WRITES its own slice
+    of the views (no image gather; the view index in the file name is the global one).  The video is then
+    assembled by rank 0 from the PNG files after a barrier."""
     kw = {} if torch_dtype is None else {"torch_dtype": torch_dtype}
     names = list(names)
+    rank, world = 0, 1
+    if sharded:
+        import torch.distributed as dist
+        from .dist import render_stream_sharded
+        if pad_to is not None:
+            raise ValueError("render_to_files: pad_to is not available in the sharded stream (pad the scenes on the host)")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        stream = render_stream_sharded(pipeline, scenes, resolution=resolution, **kw)
+    else:
+        stream = ((None, imgs) for imgs in pipeline.render_stream(scenes, resolution=resolution, pad_to=pad_to, **kw))
     k = 0
-    with FrameWriter(out_dir, workers=workers, tone_mapper=tone_mapper, keep_ldr=save_video) as fw:
-        for imgs in pipeline.render_stream(scenes, resolution=resolution, pad_to=pad_to, **kw):
+    own_video = save_video and world == 1
+    with FrameWriter(out_dir, workers=workers, tone_mapper=tone_mapper, keep_ldr=own_video) as fw:
+        for mine, imgs in stream:
             B, V = imgs.shape[0], imgs.shape[1]
+            v0 = 0 if mine is None else mine.start
             if k + B > len(names):
                 raise ValueError(f"render_to_files: {len(names)} names for more than {k + B - 1} scenes")
             for b in range(B):
                 for v in range(V):
-                    fw.submit(f"{names[k + b]}_view_{v}", imgs[b, v])
+                    fw.submit(f"{names[k + b]}_view_{v0 + v}", imgs[b, v])
             k += B
         ldr = fw.close()
         paths = list(fw.paths)
-    if save_video and ldr:
+    if own_video and ldr:
         write_mp4(os.path.join(out_dir, "video.mp4"), ldr, fps=fps)
+    elif save_video and world > 1:
+        import torch.distributed as dist
+        dist.barrier()  # every rank's frames are on disk
+        if rank == 0:
+            frames = _frames_on_disk(out_dir, names[:k])
+            if frames:
+                write_mp4(os.path.join(out_dir, "video.mp4"), [read_png(f) for f in frames], fps=fps)
     return paths
+
+
+def _frames_on_disk(out_dir: str, names: Sequence[str]) -> List[str]:
+    """`{name}_view_{v}.png` of the given scenes in (scene, view) order."""
+    out = []
+    for n in names:
+        v = 0
+        while os.path.exists(os.path.join(out_dir, f"{n}_view_{v}.png")):
+            out.append(os.path.join(out_dir, f"{n}_view_{v}.png"))
+            v += 1
+    return out

@@ -208,3 +208,55 @@ def test_render_folder_tool_orders_scenes_like_natsort(tmp_path):
     names = ["frame_10.npz", "frame_2.npz", "Frame_1.npz", "frame_02b.npz"]
     assert sorted(names, key=tool.natural_key) == ["Frame_1.npz", "frame_2.npz", "frame_02b.npz", "frame_10.npz"]
     assert tool.main(["--scene_folder", str(tmp_path), "--random_init", "tiny_swin"]) == 1  # empty folder: no GPU touched
+
+
+def _sharded_worker(rank, world, port, out_dir, q):
+    import torch.distributed as dist
+    import renderformer_b200.dist as rdist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def fake_stream(pipe, scenes, resolution=512, ldr=None, torch_dtype=None):
+            for sc in scenes:  # what dist.render_stream_sharded yields: (this rank's view slice, its frames)
+                V = sc["c2w"].shape[1]
+                mine = rdist.view_slice(V, world, rank)
+                img = torch.empty(1, mine.stop - mine.start, resolution, resolution, 3)
+                for i, v in enumerate(range(mine.start, mine.stop)):
+                    img[0, i] = float(sc["tag"]) + 0.125 * v
+                yield mine, img
+        rdist.render_stream_sharded = fake_stream
+        scenes = [dict(tag=0.0, c2w=torch.zeros(1, 3, 4, 4)), dict(tag=0.5, c2w=torch.zeros(1, 3, 4, 4))]
+        paths = fio.render_to_files(object(), iter(scenes), ["s0", "s1"], out_dir, resolution=16, save_video=True, sharded=True)
+        q.put((rank, [os.path.basename(p) for p in paths]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_to_files_sharded_world2_gloo(tmp_path):
+    """Every rank writes its own views under the GLOBAL view index; rank 0 assembles the video from the PNG files
+    after the barrier (host logic of the multi-GPU batch path, two gloo ranks on CPU)."""
+    import socket
+    import torch.multiprocessing as mp
+    pytest.importorskip("cv2")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == ["s0_view_0", "s0_view_1", "s1_view_0", "s1_view_1"] and got[1] == ["s0_view_2", "s1_view_2"]
+    for name, tag in (("s0", 0.0), ("s1", 0.5)):
+        for v in range(3):
+            assert (fio.read_exr(str(tmp_path / f"{name}_view_{v}.exr")) == np.float32(tag + 0.125 * v)).all()
+    import cv2
+    cap = cv2.VideoCapture(str(tmp_path / "video.mp4"))
+    n = 0
+    while cap.read()[0]:
+        n += 1
+    assert n == 6

@@ -9,6 +9,9 @@ usage: python tools/render_folder.py --scene_folder scenes/ --model_id /path/to/
            [--precision fp16|bf16|fp32] [--resolution 512] [--padding_length N] [--constant_texture]
            [--tone_mapper none|pbr_neutral] [--save_video] [--output_dir out/] [--workers 4]
 
+Multi-GPU: launch with torchrun (`python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1
+tools/render_folder.py ...`): the scene stage is row-sharded, every rank renders and writes its own views.
+
 `--model_id` is a local directory with config.json + model.safetensors (there is no hub access here);
 `--random_init NAME` renders with seeded random weights of a named architecture instead (smoke runs)."""
 import argparse
@@ -61,23 +64,35 @@ def main(argv=None) -> int:
         pipe = RenderFormerRenderingPipeline.from_pretrained(args.model_id)
     else:
         ap.error("one of --model_id / --random_init is required")
-    pipe.to(torch.device("cuda"))
-    pipe.cuda_graphs = args.padding_length is not None
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # one process per GPU (torchrun): both stages shard, every rank writes its own frames
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pipe.to(torch.device("cuda", local_rank))
+    pipe.cuda_graphs = args.padding_length is not None or world > 1
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.precision]
 
     def scenes():
         for p in files:  # host side of scene i+1 is prepared while scene i renders (render_stream pulls one ahead)
-            sc = scene_io.to_pipeline_inputs(scene_io.load_scene_file(p), constant_texture=args.constant_texture)
+            sc = scene_io.to_pipeline_inputs(scene_io.load_scene_file(p), constant_texture=args.constant_texture,
+                                             pad_to=args.padding_length if world > 1 else None)  # sharded stream: pad on the host
             yield {k: (v.pin_memory() if v.dtype != torch.bool else v) for k, v in sc.items()}
 
     out_dir = args.output_dir or args.scene_folder
     names = [os.path.splitext(os.path.basename(p))[0] for p in files]
     t0 = time.time()
     paths = frame_io.render_to_files(pipe, scenes(), names, out_dir, resolution=args.resolution, torch_dtype=dtype,
-                                     tone_mapper=args.tone_mapper, pad_to=args.padding_length,
-                                     save_video=args.save_video, workers=args.workers)
+                                     tone_mapper=args.tone_mapper, pad_to=args.padding_length if world == 1 else None,
+                                     save_video=args.save_video, workers=args.workers, sharded=world > 1)
     dt = time.time() - t0
-    print(f"{len(paths)} frames of {len(files)} scenes -> {out_dir} in {dt:.2f} s ({len(paths) / dt:.1f} frames/s incl. file encoding)")
+    print(f"[rank {os.environ.get('RANK', '0')}] {len(paths)} frames of {len(files)} scenes -> {out_dir} in {dt:.2f} s "
+          f"({len(paths) / dt:.1f} frames/s incl. file encoding)")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
