@@ -46,10 +46,13 @@ CASES = [
     ("large_1024_1024", "v1_1_swin_large", 1024, None, 1, 1024, 5, 7),
     ("large_8192_256", "v1_1_swin_large", 8192, None, 1, 256, 6, 7),
     ("large_b2", "v1_1_swin_large", 192, 208, 2, 128, 8, 7),
+    # BASELINE configs[0] literally: V1-Base (205M, full ray self-attention over 4096 ray tokens) on examples/cbox.json,
+    # 1 view 512^2 -- the reference's own CPU-runnable case
+    ("base_cbox_512", "v1_base", "cbox", None, 1, 512, 0, 7),
 ]
 EXTRA = {  # name -> (number of scenes in the batch, pixel stride of the stored image)
     "large_4096_512_v4": (1, 2), "large_cbox_512": (1, 1), "large_1024_1024": (1, 4), "large_8192_256": (1, 1),
-    "large_b2": (2, 1),
+    "large_b2": (2, 1), "base_cbox_512": (1, 1),
 }
 
 
