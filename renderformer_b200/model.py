@@ -60,11 +60,17 @@ class RenderFormer(nn.Module):
 
     # ---- persistence (same files as the reference's hub mixin) ----------------------
     @classmethod
-    def from_pretrained(cls, model_id: str, **_) -> "RenderFormer":
-        path = model_id
+    def from_pretrained(cls, pretrained_model_name_or_path, *, force_download: bool = False, token=None,
+                        cache_dir=None, local_files_only: bool = False, revision: Optional[str] = None,
+                        **model_kwargs) -> "RenderFormer":
+        """Signature of huggingface_hub's PyTorchModelHubMixin.from_pretrained, which the reference class inherits
+        (models/renderformer.py:13): a local directory with config.json + model.safetensors, or a hub id (the hub
+        options are handed to `snapshot_download`; needs network, not used in tests)."""
+        path = str(pretrained_model_name_or_path)
         if not os.path.isdir(path):
-            from huggingface_hub import snapshot_download  # needs network; not used in tests
-            path = snapshot_download(model_id)
+            from huggingface_hub import snapshot_download
+            path = snapshot_download(path, force_download=force_download, token=token, cache_dir=cache_dir,
+                                     local_files_only=local_files_only, revision=revision)
         with open(os.path.join(path, "config.json")) as f:
             cfg = RenderFormerConfig.from_dict(json.load(f))
         model = cls(cfg)

@@ -1,0 +1,110 @@
+"""CPU, build container only: the drop-in package keeps the reference's call surface -- every class and
+function under the reference's module paths exists here with the same constructor / forward parameter names, order and
+defaults.  The reference's signatures are read live from the unmodified reference (baseline/_ref or /root/reference)
+in a subprocess (two packages named `renderformer` cannot share one interpreter); ours may only ADD optional
+parameters behind the reference's."""
+import importlib
+import inspect
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SURFACE = {
+    "renderformer": ["RenderFormerRenderingPipeline", "RenderFormer"],
+    "renderformer.layers.attention": ["TransformerEncoder", "TransformerDecoder", "AttentionLayer", "MultiHeadAttention",
+                                      "SwinSelfAttention", "FeedForwardSwiGLU"],
+    "renderformer.layers.dpt": ["DPTHead"],
+    "renderformer.models.view_transformer": ["ViewTransformer"],
+    "renderformer.models.renderformer": ["RenderFormer"],
+    "renderformer.models.config": ["RenderFormerConfig"],
+    "renderformer.encodings.rope": ["TriangleRotaryEmbedding", "apply_rotary_emb_cossin", "apply_rotary_emb_one_cossin",
+                                    "freqs_to_cos_sin", "rotate_half_hf"],
+    "renderformer.encodings.nerf_encoding": ["NeRFEncoding"],
+    "renderformer.utils.ray_generator": ["RayGenerator"],
+    "renderformer.utils.transform": ["trans_to_cam_coord"],
+    "renderformer.pipelines.rendering_pipeline": ["RenderFormerRenderingPipeline"],
+}
+METHODS = ("forward", "render", "to", "from_pretrained", "process_tri_vpos_list", "construct_seq")
+
+HELPERS = r'''
+import importlib, inspect, json
+def _params(f):
+    try:
+        return [[p.name, None if p.default is inspect._empty else repr(p.default), p.kind.name]
+                for p in inspect.signature(f).parameters.values()]
+    except (TypeError, ValueError):
+        return None
+def surface(spec, methods):
+    out = {}
+    for mod, names in spec.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            obj = getattr(m, n, None)
+            if obj is None:
+                out[mod + "." + n] = None
+            elif inspect.isclass(obj):
+                d = {"__init__": _params(obj.__init__)}
+                for meth in methods:
+                    if hasattr(obj, meth):
+                        d[meth] = _params(getattr(obj, meth))
+                out[mod + "." + n] = d
+            else:
+                out[mod + "." + n] = {"call": _params(obj)}
+    return out
+'''
+
+
+def _reference_present():
+    return any(os.path.isdir(os.path.join(p, "renderformer", "models"))
+               for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"))
+
+
+@pytest.mark.skipif(not _reference_present(), reason="no reference here (baseline/_ref and /root/reference absent)")
+def test_module_tree_and_signatures_match_the_reference():
+    worker = ("import sys, json\nsys.path.insert(0, %r)\nfrom oracle.reference_loader import load_reference\n"
+              "load_reference('sdpa')\n" % ROOT) + HELPERS + \
+             "print('SIG_JSON ' + json.dumps(surface(%r, %r)))\n" % (SURFACE, METHODS)
+    r = subprocess.run([sys.executable, "-c", worker], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("SIG_JSON ")]
+    assert r.returncode == 0 and lines, r.stderr[-2000:]
+    ref = json.loads(lines[-1][len("SIG_JSON "):])
+
+    ns = {}
+    exec(HELPERS, ns)
+    import renderformer
+    assert os.path.abspath(renderformer.__file__).startswith(os.path.join(ROOT, "renderformer") + os.sep)
+    ours = ns["surface"](SURFACE, METHODS)
+
+    problems = []
+    for name, rsig in ref.items():
+        assert rsig is not None, f"{name} not in the reference?"
+        osig = ours.get(name)
+        if osig is None:
+            problems.append(f"{name}: missing")
+            continue
+        for meth, rp in rsig.items():
+            op = osig.get(meth)
+            if op is None:
+                problems.append(f"{name}.{meth}: missing")
+                continue
+            if rp is None:
+                continue
+            if any(p[2] == "VAR_POSITIONAL" for p in op) and len(rp) == 1:
+                continue  # reference takes no arguments; ours tolerates any (RayGenerator())
+            names_r, names_o = [p[0] for p in rp], [p[0] for p in op]
+            if names_o[:len(rp)] != names_r:
+                problems.append(f"{name}.{meth}: reference {names_r} vs ours {names_o}")
+                continue
+            # where the reference has a default ours has the same one; ours may be more lenient (extra defaults,
+            # extra optional parameters behind the reference's)
+            for pr, po in zip(rp, op):
+                if pr[1] is not None and pr[1] != po[1]:
+                    problems.append(f"{name}.{meth}: default of {pr[0]} is {pr[1]} in the reference, {po[1]} here")
+            if any(p[1] is None and p[2] not in ("VAR_POSITIONAL", "VAR_KEYWORD") for p in op[len(rp):]):
+                problems.append(f"{name}.{meth}: extra parameters without defaults {names_o[len(rp):]}")
+    assert not problems, "\n".join(problems)
