@@ -674,6 +674,8 @@ class ResidualConvUnit(nn.Module):
         super().__init__()
         self.conv1 = nn.Conv2d(features, features, kernel_size=3, stride=1, padding=1, bias=True)
         self.conv2 = nn.Conv2d(features, features, kernel_size=3, stride=1, padding=1, bias=True)
+        if activation is not None:  # same attribute path as the reference (:74); the kernels apply SiLU themselves
+            self.activation = activation
 
 
 class FeatureFusionBlock(nn.Module):
@@ -682,9 +684,10 @@ class FeatureFusionBlock(nn.Module):
     def __init__(self, features, no_resconv1: bool = False):
         super().__init__()
         self.out_conv = nn.Conv2d(features, features, kernel_size=1, stride=1, padding=0, bias=True)
+        act = nn.SiLU(False)  # one instance per block, shared by its units (layers/dpt.py:128-129,162-171)
         if not no_resconv1:
-            self.resConvUnit1 = ResidualConvUnit(features)
-        self.resConvUnit2 = ResidualConvUnit(features)
+            self.resConvUnit1 = ResidualConvUnit(features, act)
+        self.resConvUnit2 = ResidualConvUnit(features, act)
 
 
 class DPTHead(nn.Module, _EngineBacked):

@@ -108,3 +108,33 @@ def test_module_tree_and_signatures_match_the_reference():
             if any(p[1] is None and p[2] not in ("VAR_POSITIONAL", "VAR_KEYWORD") for p in op[len(rp):]):
                 problems.append(f"{name}.{meth}: extra parameters without defaults {names_o[len(rp):]}")
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.skipif(not _reference_present(), reason="no reference here (baseline/_ref and /root/reference absent)")
+@pytest.mark.parametrize("arch", ["v1_base", "v1_1_swin_large"])
+def test_state_dict_and_module_paths_match_the_reference(arch):
+    """Same parameter / buffer names, shapes and dtypes, and the same sub-module attribute paths (what checkpoints,
+    `model.view_transformer.transformer.layers[3]`-style user code and `apply_kernels`-style hooks rely on),
+    for both released architectures -- built on the meta device, nothing is allocated."""
+    worker = ("import sys, json, torch\nsys.path.insert(0, %r)\nfrom oracle.reference_loader import load_reference\n"
+              "RefConfig, RefModel, _, _ = load_reference('sdpa')\n"
+              "from renderformer_b200.config import RenderFormerConfig\n"
+              "cfg = RenderFormerConfig.named(%r)\n"
+              "with torch.device('meta'):\n    m = RefModel(RefConfig(**cfg.to_dict()))\n"
+              "print('TREE_JSON ' + json.dumps({'sd': {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()},\n"
+              "      'mods': sorted(n for n, _ in m.named_modules())}))\n" % (ROOT, arch))
+    r = subprocess.run([sys.executable, "-c", worker], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("TREE_JSON ")]
+    assert r.returncode == 0 and lines, r.stderr[-2000:]
+    ref = json.loads(lines[-1][len("TREE_JSON "):])
+
+    import torch
+    from renderformer_b200.config import RenderFormerConfig
+    from renderformer_b200.model import RenderFormer
+    ours = RenderFormer(RenderFormerConfig.named(arch))
+    sd = {k: [list(v.shape), str(v.dtype)] for k, v in ours.state_dict().items()}
+    assert sorted(sd) == sorted(ref["sd"])
+    assert sd == ref["sd"]
+    mods = sorted(n for n, _ in ours.named_modules())
+    missing = [n for n in ref["mods"] if n not in mods]
+    assert not missing, f"sub-module paths of the reference that do not exist here: {missing[:10]}"
