@@ -138,3 +138,21 @@ def test_state_dict_and_module_paths_match_the_reference(arch):
     mods = sorted(n for n, _ in ours.named_modules())
     missing = [n for n in ref["mods"] if n not in mods]
     assert not missing, f"sub-module paths of the reference that do not exist here: {missing[:10]}"
+
+
+@pytest.mark.skipif(not _reference_present(), reason="no reference here (baseline/_ref and /root/reference absent)")
+def test_config_fields_and_defaults_match_the_reference():
+    """config.json is the flat dict of the reference's dataclass (models/config.py:5-92): same field names, order and
+    default values, so a checkpoint's config round-trips through either implementation."""
+    worker = ("import sys, json, dataclasses\nsys.path.insert(0, %r)\nfrom oracle.reference_loader import load_reference\n"
+              "RefConfig, _, _, _ = load_reference('sdpa')\n"
+              "print('CFG_JSON ' + json.dumps([[f.name, repr(getattr(RefConfig(), f.name))] for f in dataclasses.fields(RefConfig)]))\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", worker], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("CFG_JSON ")]
+    assert r.returncode == 0 and lines, r.stderr[-2000:]
+    ref = json.loads(lines[-1][len("CFG_JSON "):])
+    import dataclasses
+    from renderformer_b200.config import RenderFormerConfig
+    ours = [[f.name, repr(getattr(RenderFormerConfig(), f.name))] for f in dataclasses.fields(RenderFormerConfig)]
+    assert [n for n, _ in ours] == [n for n, _ in ref]
+    assert ours == ref
