@@ -94,3 +94,39 @@ def test_encoder_key_split_rule():
         n_tiles = (ntp + 127) // 128
         assert kst > 0 and -(-n_tiles // kst) == chunks, (ntp, kst)
         assert kst * chunks >= n_tiles and kst * (chunks - 1) < n_tiles   # every chunk holds at least one tile
+
+
+def test_precision_argument_follows_the_reference():
+    """rendering_pipeline.py:98: bfloat16 / float16 / float32 are accepted, anything else fails the same assertion;
+    float32 maps to fp16 operands and warns once (there is no fp32 tensor-core path)."""
+    import warnings
+    import pytest
+    import torch
+    from renderformer_b200 import model as M
+    assert M.operand_dtype(torch.bfloat16) == torch.bfloat16 and M.operand_dtype(torch.float16) == torch.float16
+    with pytest.raises(AssertionError, match="Invalid precision"):
+        M.operand_dtype(torch.float64)
+    M._warned_fp32[0] = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert M.operand_dtype(torch.float32) == torch.float16 and M.operand_dtype(torch.float32) == torch.float16
+    assert len([x for x in w if "float32" in str(x.message)]) == 1
+
+
+def test_no_cpu_fallback_errors_are_loud():
+    """The product path has no CPU fallback: a pipeline on the CPU refuses to render instead of computing elsewhere."""
+    import pytest
+    import torch
+    from renderformer_b200 import lib
+    from renderformer_b200.config import RenderFormerConfig
+    from renderformer_b200.model import RenderFormer, RenderFormerRenderingPipeline
+    from renderformer_b200.synth import init_state_dict, make_scene
+    cfg = RenderFormerConfig.named("tiny_swin")
+    model = RenderFormer(cfg)
+    model.load_state_dict(init_state_dict(cfg, 1))
+    pipe = RenderFormerRenderingPipeline(model)
+    sc = make_scene(8, 1, seed=0)
+    with pytest.raises(lib.RfbError, match="CUDA"):
+        pipe(sc["triangles"], sc["texture"], sc["mask"], sc["vn"], sc["c2w"], sc["fov"], resolution=64)
+    with pytest.raises(lib.RfbError, match="CUDA"):
+        next(pipe.render_stream([sc], resolution=64))
