@@ -87,3 +87,35 @@ def test_broadcast_and_gather_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+def _worker_few_views(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        V = 1  # fewer views than ranks: rank 1 owns an empty slice and still takes part in the gather
+        sizes = [view_slice(V, world, r).stop - view_slice(V, world, r).start for r in range(world)]
+        mine = view_slice(V, world, rank)
+        img = torch.full((mine.stop - mine.start, 2, 2, 3), 7.0)
+        out = gather_images(img, dst=0, sizes=sizes)
+        ok = sizes == [1, 0] and img.shape[0] == (1 if rank == 0 else 0)
+        ok = ok and ((out.shape == (1, 2, 2, 3) and bool((out == 7.0).all())) if rank == 0 else out is None)
+        h = gather_images(img, dst=0, sizes=sizes, async_op=True)  # the asynchronous form bench.py uses
+        out2 = h.wait()
+        ok = ok and ((out2.shape == (1, 2, 2, 3)) if rank == 0 else out2 is None)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_fewer_views_than_ranks_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_few_views, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
