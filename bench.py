@@ -540,7 +540,7 @@ def main():
             att = by.get("attention", [0.0, 1.0, 1])
             ach = g[0] / g[1] / 1e12
             traffic, traffic_src = None, None
-            for name in ("r02_gemm_traffic.json", "r01e_gemm_traffic.json"):
+            for name in ("r02b_gemm_traffic.json", "r02_gemm_traffic.json", "r01e_gemm_traffic.json"):  # newest capture first
                 tpath = os.path.join(ROOT, "profiles", name)
                 want_chunk = 8 if name.startswith("r02") else 4
                 if os.path.exists(tpath) and args.config == "v1_1_swin_large" and (N, R, pipe.view_chunk) == (4096, 512, want_chunk):
