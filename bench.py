@@ -90,7 +90,15 @@ def workload_text(args, world):
     V = job_views(args, world)
     kind = (f"{args.views_per_gpu} views on every GPU (weak scaling)" if args.views_per_gpu > 0 else
             f"fixed job of {V} views (strong scaling; BASELINE configs[2] at 32)")
-    return (f"{args.config} (483M, random-init weights, seed 7), synthetic {args.tris}-triangle scene (seed 0), "
+    try:  # parameter count of the named architecture (483M for the metric's v1_1_swin_large)
+        import math
+        from renderformer_b200.config import RenderFormerConfig
+        from renderformer_b200.synth import state_dict_shapes
+        n_par = sum(math.prod(s) for s in state_dict_shapes(RenderFormerConfig.named(args.config)).values())
+        size = f"{n_par / 1e6:.0f}M" if n_par >= 1e6 else f"{n_par / 1e3:.0f}k"
+    except Exception:  # noqa: BLE001
+        size = "?"
+    return (f"{args.config} ({size}, random-init weights, seed 7), synthetic {args.tris}-triangle scene (seed 0), "
             f"{args.resolution}x{args.resolution}, one scene + {V}-view camera orbit per step: {kind}")
 
 
