@@ -260,3 +260,59 @@ def test_render_to_files_sharded_world2_gloo(tmp_path):
     while cap.read()[0]:
         n += 1
     assert n == 6
+
+
+class _EchoPipeline:
+    """Stand-in with the pipeline attributes the tool touches; "renders" the mean diffuse colour of the valid triangles so
+    that the files prove which scene / padding / texture form reached render_stream."""
+    cuda_graphs = False
+
+    def __init__(self):
+        self.seen = []
+
+    def render_stream(self, scenes, resolution=512, torch_dtype=None, ldr=None, pad_to=None):
+        for sc in scenes:
+            self.seen.append({k: tuple(v.shape) for k, v in sc.items()} | {"pad_to": pad_to, "dtype": torch_dtype})
+            B, V = sc["c2w"].shape[:2]
+            tex = sc["texture"]
+            diffuse = tex[0, :, :3] if tex.dim() == 3 else tex[0, :, :3, 0, 0]
+            colour = diffuse[sc["mask"][0]].mean(dim=0)
+            yield colour.view(1, 1, 1, 1, 3).expand(B, V, resolution, resolution, 3).contiguous()
+
+
+@pytest.mark.parametrize("flags", [[], ["--constant_texture"], ["--padding_length", "32"]],
+                         ids=["texel-grid", "constant-texture", "padded"])
+def test_render_folder_tool_host_logic(tmp_path, flags):
+    """tools/render_folder.py end to end on the CPU with a stand-in pipeline: natural file order, scene loading,
+    texture form, padding flag, precision, file names and contents."""
+    import importlib.util
+    from renderformer_b200 import scene_io as sio
+    from renderformer_b200.synth import make_scene
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("render_folder", os.path.join(root, "tools", "render_folder.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    folder = tmp_path / "scenes"
+    folder.mkdir()
+    want = {}
+    for name, n in (("frame_10", 9), ("frame_2", 14)):
+        sc = make_scene(n, 2, seed=n)
+        tex13 = sc["texture"][0, :, :, 0, 0].numpy()
+        sio.save_npz({"triangles": sc["triangles"][0].numpy(), "vn": sc["vn"][0].numpy(), "tex13": tex13,
+                      "c2w": sc["c2w"][0].numpy(), "fov": sc["fov"][0, :, 0].numpy()}, str(folder / f"{name}.npz"))
+        want[name] = tex13[:, :3].mean(axis=0)
+    pipe = _EchoPipeline()
+    out = tmp_path / "out"
+    rc = tool.main(["--scene_folder", str(folder), "--random_init", "tiny_swin", "--precision", "bf16", "--resolution", "16",
+                    "--output_dir", str(out)] + flags, _pipeline=pipe)
+    assert rc == 0
+    assert [s["triangles"][1] for s in pipe.seen] == [14, 9]                       # frame_2 before frame_10 (natural order)
+    assert all(s["dtype"] == torch.bfloat16 for s in pipe.seen)
+    assert all(s["pad_to"] == (32 if "--padding_length" in flags else None) for s in pipe.seen)
+    assert all(len(s["texture"]) == (3 if "--constant_texture" in flags else 5) for s in pipe.seen)
+    assert pipe.cuda_graphs == ("--padding_length" in flags)
+    for name, colour in want.items():
+        for v in range(2):
+            hdr = fio.read_exr(str(out / f"{name}_view_{v}.exr"))
+            assert hdr.shape == (16, 16, 3) and np.allclose(hdr[3, 5], colour, atol=1e-6)
+            assert np.array_equal(fio.read_png(str(out / f"{name}_view_{v}.png")), (np.clip(hdr, 0, 1) * 255).astype(np.uint8))

@@ -29,7 +29,8 @@ def natural_key(s: str):
     return [int(t) if t.isdigit() else t.lower() for t in re.split(r"(\d+)", s)]
 
 
-def main(argv=None) -> int:
+def main(argv=None, _pipeline=None) -> int:
+    """`_pipeline`: a ready pipeline object (tests inject a stand-in; the host logic then runs without a GPU)."""
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--scene_folder", required=True)
     ap.add_argument("--model_id", default=None)
@@ -53,7 +54,9 @@ def main(argv=None) -> int:
     if not files:
         print(f"no .npz / .h5 scenes in {args.scene_folder} (convert scene JSON files with tools/convert_scene.py)")
         return 1
-    if args.random_init:
+    if _pipeline is not None:
+        pipe = _pipeline
+    elif args.random_init:
         from renderformer_b200.config import RenderFormerConfig
         from renderformer_b200.synth import init_state_dict
         cfg = RenderFormerConfig.named(args.random_init)
@@ -70,15 +73,17 @@ def main(argv=None) -> int:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    pipe.to(torch.device("cuda", local_rank))
+    if _pipeline is None:
+        pipe.to(torch.device("cuda", local_rank))
     pipe.cuda_graphs = args.padding_length is not None or world > 1
+    pin = torch.cuda.is_available()
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.precision]
 
     def scenes():
         for p in files:  # host side of scene i+1 is prepared while scene i renders (render_stream pulls one ahead)
             sc = scene_io.to_pipeline_inputs(scene_io.load_scene_file(p), constant_texture=args.constant_texture,
                                              pad_to=args.padding_length if world > 1 else None)  # sharded stream: pad on the host
-            yield {k: (v.pin_memory() if v.dtype != torch.bool else v) for k, v in sc.items()}
+            yield {k: (v.pin_memory() if pin and v.dtype != torch.bool else v) for k, v in sc.items()}
 
     out_dir = args.output_dir or args.scene_folder
     names = [os.path.splitext(os.path.basename(p))[0] for p in files]
