@@ -49,10 +49,14 @@ CASES = [
     # BASELINE configs[0] literally: V1-Base (205M, full ray self-attention over 4096 ray tokens) on examples/cbox.json,
     # 1 view 512^2 -- the reference's own CPU-runnable case
     ("base_cbox_512", "v1_base", "cbox", None, 1, 512, 0, 7),
+    # corners of the BASELINE configs[4] sweep (triangles 512-4096 x resolution 256^2-1024^2) not covered above
+    ("large_512_256", "v1_1_swin_large", 512, None, 1, 256, 9, 7),
+    ("large_2048_512", "v1_1_swin_large", 2048, None, 2, 512, 10, 7),
+    ("large_4096_1024", "v1_1_swin_large", 4096, None, 1, 1024, 0, 7),
 ]
 EXTRA = {  # name -> (number of scenes in the batch, pixel stride of the stored image)
     "large_4096_512_v4": (1, 2), "large_cbox_512": (1, 1), "large_1024_1024": (1, 4), "large_8192_256": (1, 1),
-    "large_b2": (2, 1), "base_cbox_512": (1, 1),
+    "large_b2": (2, 1), "base_cbox_512": (1, 1), "large_512_256": (1, 1), "large_2048_512": (1, 2), "large_4096_1024": (1, 4),
 }
 
 
@@ -121,7 +125,7 @@ def main():
         rng = (ref_img.min().item(), ref_img.max().item())
         print(f"{name}: oracle-vs-reference max|d| image {d_img:.3e} (range {rng[0]:.4f}..{rng[1]:.4f}) seq {d_seq:.3e}")
         assert d_img <= 2e-4 * max(1.0, abs(rng[1])), "oracle restatement disagrees with the reference"
-        big = n_real >= 1024  # keep the full-size fixture small: image + every 16th seq row as fp16
+        big = n_real >= 1024 or name == "large_512_256"  # keep the full-size fixtures small: image + every 16th seq row as fp16
         np.savez_compressed(
             os.path.join(out_dir, f"{name}.npz"),
             hdr=ref_img.float().numpy()[:, :, ::hdr_stride, ::hdr_stride],
