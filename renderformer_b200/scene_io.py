@@ -242,6 +242,20 @@ def expand_texture(tex13: np.ndarray, size: int = TEXELS) -> np.ndarray:
     return (tex13[:, :, None, None] * texel_mask(size)[None, None]).astype(np.float32)
 
 
+def constant_texture_of(texture: np.ndarray, atol: float = 0.0) -> Optional[np.ndarray]:
+    """[N,C,P,P] texel grid -> [N,C] per-triangle constants if the grid IS "constants times the triangular texel mask
+    x + y <= P" (every scene written by scene_processor/to_h5.py:37-66), else None.  Lets a caller that holds the
+    reference's 218 MB texel grid take the constant-texture fast path without being told so."""
+    tex = np.asarray(texture)
+    if tex.ndim != 4 or tex.shape[2] != tex.shape[3]:
+        return None
+    m = texel_mask(tex.shape[2])
+    consts = tex[:, :, 0, 0]
+    inside_ok = np.abs(tex[:, :, m] - consts[:, :, None]).max(initial=0.0) <= atol
+    outside_ok = np.abs(tex[:, :, ~m]).max(initial=0.0) <= atol
+    return np.ascontiguousarray(consts) if (inside_ok and outside_ok) else None
+
+
 def to_pipeline_inputs(scene: Dict[str, np.ndarray], pad_to: Optional[int] = None, constant_texture: bool = False):
     """Batch-1 torch tensors with the pipeline's argument names.  `constant_texture=True` keeps the
     texture as [1,N,13] per-triangle constants (the pipeline's fast path: no 32x32 expansion, no
@@ -259,9 +273,14 @@ def to_pipeline_inputs(scene: Dict[str, np.ndarray], pad_to: Optional[int] = Non
         tex = tex13 if constant_texture else expand_texture(tex13)
     else:  # a stored texel grid (load_h5): arbitrary textures, no constant-texture shortcut
         if constant_texture:
-            raise ValueError("constant_texture needs per-triangle constants ('tex13'); this scene stores a texel grid")
-        tex = np.zeros((total,) + tuple(scene["texture"].shape[1:]), np.float32)
-        tex[:n] = scene["texture"]
+            consts = constant_texture_of(scene["texture"])
+            if consts is None:
+                raise ValueError("constant_texture: this scene's texel grid is not 'constants times the triangular mask'")
+            tex13[:n] = consts
+            tex = tex13
+        else:
+            tex = np.zeros((total,) + tuple(scene["texture"].shape[1:]), np.float32)
+            tex[:n] = scene["texture"]
     return {
         "triangles": torch.from_numpy(tri)[None], "texture": torch.from_numpy(tex)[None],
         "mask": torch.from_numpy(mask)[None], "vn": torch.from_numpy(vn)[None],

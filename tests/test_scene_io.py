@@ -190,8 +190,19 @@ def test_scene_file_loader_dispatch(tmp_path, monkeypatch):
     inp = sio.to_pipeline_inputs(got, pad_to=8)
     assert tuple(inp["texture"].shape) == (1, 8, 13, 32, 32) and inp["mask"][0].tolist() == [True] * 5 + [False] * 3
     assert np.array_equal(inp["texture"][0, :5].numpy(), grid.astype(np.float32)) and not inp["texture"][0, 5:].any()
+    # the stored grid IS constants x mask: the fast path is detected, fp16 rounding of the file included
+    fast = sio.to_pipeline_inputs(got, constant_texture=True)
+    assert tuple(fast["texture"].shape) == (1, 5, 13)
+    assert np.array_equal(fast["texture"][0].numpy(), sc["tex13"].astype(np.float16).astype(np.float32))
+    assert np.array_equal(sio.constant_texture_of(got["texture"]), fast["texture"][0].numpy())
+    painted = dict(got, texture=got["texture"].copy())
+    painted["texture"][2, 0, 3, 4] += 0.25  # an arbitrary (non-constant) texture keeps the full path
+    assert sio.constant_texture_of(painted["texture"]) is None
     with pytest.raises(ValueError, match="constant_texture"):
-        sio.to_pipeline_inputs(got, constant_texture=True)
+        sio.to_pipeline_inputs(painted, constant_texture=True)
+    leaky = dict(got, texture=got["texture"].copy())
+    leaky["texture"][1, 5, 31, 31] = 0.5    # a texel outside the triangular mask
+    assert sio.constant_texture_of(leaky["texture"]) is None
 
 
 EXAMPLE_TRIANGLES = {  # triangle counts of the reference's example scenes as converted here (cbox: SURVEY §8d, 5633)
