@@ -409,6 +409,49 @@ class FrameWriter:
         return False
 
 
+def prefetch(iterable: Iterable, depth: int = 2):
+    """Run `iterable` (e.g. a generator that loads a scene file, expands its 218 MB texel grid and pins it) on a
+    background thread, `depth` items ahead of the consumer: the input side of the batch path off the critical path
+    (batch_infer.py:103-110 uses DataLoader workers for this).  Order is kept; an exception in the producer is
+    re-raised in the consumer at the position where it happened; closing the generator stops the thread."""
+    import queue
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+    stop = threading.Event()
+    END, ERR = object(), object()
+
+    def put(item) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def run():
+        try:
+            for item in iterable:
+                if not put(item):
+                    return
+            put(END)
+        except BaseException as e:  # noqa: BLE001  (handed to the consumer)
+            put((ERR, e))
+
+    t = threading.Thread(target=run, name="rfb-prefetch", daemon=True)
+    t.start()
+    try:
+        while True:
+            item = q.get()
+            if item is END:
+                return
+            if isinstance(item, tuple) and len(item) == 2 and item[0] is ERR:
+                raise item[1]
+            yield item
+    finally:
+        stop.set()
+        t.join(timeout=5)
+
+
 def render_to_files(pipeline, scenes: Iterable[dict], names: Sequence[str], out_dir: str, resolution: int = 512,
                     torch_dtype=None, tone_mapper: str = "none", pad_to: Optional[int] = None,
                     save_video: bool = False, workers: int = 4, fps: int = 24, sharded: bool = False) -> List[str]:

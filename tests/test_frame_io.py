@@ -316,3 +316,38 @@ def test_render_folder_tool_host_logic(tmp_path, flags):
             hdr = fio.read_exr(str(out / f"{name}_view_{v}.exr"))
             assert hdr.shape == (16, 16, 3) and np.allclose(hdr[3, 5], colour, atol=1e-6)
             assert np.array_equal(fio.read_png(str(out / f"{name}_view_{v}.png")), (np.clip(hdr, 0, 1) * 255).astype(np.uint8))
+
+
+def test_prefetch_keeps_order_overlaps_and_propagates_errors():
+    import threading
+    import time
+    made = []
+
+    def slow_source(n, fail_at=None):
+        for i in range(n):
+            time.sleep(0.02)
+            if i == fail_at:
+                raise KeyError(f"scene {i}")
+            made.append((i, threading.current_thread().name))
+            yield i
+
+    got, lead = [], []
+    for x in fio.prefetch(slow_source(10), depth=2):
+        time.sleep(0.03)  # the consumer's own work overlaps the producer's
+        got.append(x)
+        lead.append(len(made) - len(got))  # items the producer has finished beyond the ones consumed
+    assert got == list(range(10)) and all(name == "rfb-prefetch" for _, name in made)
+    assert max(lead) >= 1  # the producer ran ahead while the consumer was busy
+    with pytest.raises(KeyError, match="scene 3"):
+        out = []
+        for x in fio.prefetch(slow_source(10, fail_at=3)):
+            out.append(x)
+    assert out == [0, 1, 2]
+    # closing early stops the producer thread
+    made.clear()
+    g = fio.prefetch(slow_source(1000), depth=1)
+    assert next(g) == 0
+    g.close()
+    n = len(made)
+    time.sleep(0.1)
+    assert len(made) <= n + 1 and not [t for t in threading.enumerate() if t.name == "rfb-prefetch" and t.is_alive()]

@@ -88,7 +88,8 @@ def main(argv=None, _pipeline=None) -> int:
     out_dir = args.output_dir or args.scene_folder
     names = [os.path.splitext(os.path.basename(p))[0] for p in files]
     t0 = time.time()
-    paths = frame_io.render_to_files(pipe, scenes(), names, out_dir, resolution=args.resolution, torch_dtype=dtype,
+    # scene files are read / expanded / pinned two scenes ahead on a background thread
+    paths = frame_io.render_to_files(pipe, frame_io.prefetch(scenes(), depth=2), names, out_dir, resolution=args.resolution, torch_dtype=dtype,
                                      tone_mapper=args.tone_mapper, pad_to=args.padding_length if world == 1 else None,
                                      save_video=args.save_video, workers=args.workers, sharded=world > 1)
     dt = time.time() - t0
