@@ -1,17 +1,17 @@
 #!/usr/bin/env python
-"""Where does the image error of the CUDA path come from?  (GPU box; development tool, not on the product path.)
+"""Where does the image error of the CUDA path come from?  (GPU box; test infrastructure: uses the oracle as the checker; not on the product path.)
 
 Runs the fp32 CPU oracle and the CUDA engine on one scene and compares stage by stage, then swaps stages:
   A  ours end to end
   B  our decoder + DPT on the ORACLE's encoder output        (isolates the view stage)
   C  our DPT on the ORACLE's decoder features                 (isolates the DPT head)
   D  the ORACLE's DPT on OUR decoder features                 (our transformer stacks without our DPT)
-usage: python tools/error_budget.py [cbox | <n_tris>] [resolution] [config]
+usage: python tests/diagnostics/error_budget.py [cbox | <n_tris>] [resolution] [config]
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

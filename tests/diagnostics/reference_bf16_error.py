@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""What does bf16 cost the REFERENCE ITSELF?  (CPU; development / documentation tool, imports the unmodified
+"""What does bf16 cost the REFERENCE ITSELF?  (CPU; test infrastructure, imports the unmodified
 reference through oracle/reference_loader.py.)
 
 Renders one scene with the unmodified reference twice -- `torch_dtype=float32` (the grading reference) and
@@ -7,12 +7,12 @@ Renders one scene with the unmodified reference twice -- `torch_dtype=float32` (
 them) -- with the same seeded weights, and prints the north_star metrics of the second against the first.  This is
 the error floor of "bf16 tensor-core math" for that scene: a from-scratch bf16 implementation cannot be expected to
 sit far below it.
-usage: python tools/reference_bf16_error.py [cbox | <n_tris>] [resolution] [config]"""
+usage: python tests/diagnostics/reference_bf16_error.py [cbox | <n_tris>] [resolution] [config]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

@@ -56,9 +56,9 @@ def _cases(golden_dir):
 # Two operand formats (pipeline `torch_dtype`): fp16 is the reference CLIs' default precision, bf16 is what
 # the north_star names and bench.py runs.  Both meet the north_star tolerance on every fixture except ONE:
 # the cbox scene (5633 triangles) in bf16, where the worst of 786k pixels is off by 2.3e-2 of the image maximum
-# (PSNR 58.7 dB) -- bf16 rounding noise of the encoder stack, not a defect (tools/error_budget.py: the same
+# (PSNR 58.7 dB) -- bf16 rounding noise of the encoder stack, not a defect (tests/diagnostics/error_budget.py: the same
 # scene in fp16 is ~8x closer; the UNMODIFIED reference under bf16 autocast is at 2.9e-2 / 51.0 dB on this scene against
-# its own fp32 render, tools/reference_bf16_error.py).  BASELINE configs[1] is therefore quoted in fp16 (`infer.py`'s
+# its own fp32 render, tests/diagnostics/reference_bf16_error.py).  BASELINE configs[1] is therefore quoted in fp16 (`infer.py`'s
 # default precision); the bf16 run of that fixture is held to 3e-2 and printed.
 BF16_KNOWN = {"large_cbox_512": 3e-2}
 
