@@ -87,3 +87,36 @@ def test_to_h5_half_of_the_converter_equals_the_reference(scene, tmp_path):
     assert np.array_equal(ref["fov"], ours["fov"])
     # and the reference's own texel grid IS "constants x mask": the fast path's detector agrees
     assert np.array_equal(sio.constant_texture_of(ref["texture"].astype(np.float32)), ours["tex13"])
+
+
+NORM_WORKER = r"""
+import sys, types
+import numpy as np
+for name in ("trimesh", "trimesh.visual", "h5py", "pymeshlab"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["trimesh"].visual = sys.modules["trimesh.visual"]
+sys.modules["trimesh"].Trimesh = object
+sys.path.insert(0, %(ref)r)
+from scene_processor.scene_mesh import normalize_to_unit_sphere   # the reference's (scene_mesh.py:12-18), pure numpy
+mesh = types.SimpleNamespace(vertices=np.load(sys.argv[1]))
+np.save(sys.argv[2], normalize_to_unit_sphere(mesh).vertices)
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "scene_processor")), reason="the reference only exists in the build container")
+def test_normalisation_equals_the_reference(tmp_path):
+    """scene_mesh.py:12-18 run live on the vertices of a shipped OBJ: centre on the vertex mean, scale so that the
+    farthest vertex sits at radius 0.5."""
+    from renderformer_b200 import scene_io as sio
+    obj_path = os.path.join(REF, "examples", "objects", "cbox", "tall-box.obj")
+    verts, faces = sio.load_obj(obj_path)
+    np.save(str(tmp_path / "v.npy"), verts)
+    r = subprocess.run([sys.executable, "-c", NORM_WORKER % {"ref": REF}, str(tmp_path / "v.npy"), str(tmp_path / "n.npy")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref_tris = np.load(str(tmp_path / "n.npy"))[faces]
+    obj = {"mesh_path": obj_path, "transform": {"translation": [0, 0, 0], "rotation": [0, 0, 0], "scale": [1, 1, 1], "normalize": True},
+           "material": {"diffuse": [0.5, 0.5, 0.5], "specular": [0, 0, 0], "roughness": 0.5, "emissive": [0, 0, 0], "smooth_shading": False}}
+    tris, _, _ = sio._object_mesh(obj, "/")
+    assert np.array_equal(tris, ref_tris)
+    assert abs(np.linalg.norm(tris.reshape(-1, 3), axis=-1).max() - 0.5) < 1e-12
