@@ -120,3 +120,54 @@ def test_normalisation_equals_the_reference(tmp_path):
     tris, _, _ = sio._object_mesh(obj, "/")
     assert np.array_equal(tris, ref_tris)
     assert abs(np.linalg.norm(tris.reshape(-1, 3), axis=-1).max() - 0.5) < 1e-12
+
+
+DATASET_WORKER = r"""
+import sys, types
+import numpy as np
+class _H5:
+    def __init__(self, path, mode="r"): self.d = np.load(path)
+    def __enter__(self): return self.d
+    def __exit__(self, *a): self.d.close()
+h5py = types.ModuleType("h5py"); h5py.File = _H5
+imageio = types.ModuleType("imageio")
+natsort = types.ModuleType("natsort"); natsort.natsorted = sorted
+ocio = types.ModuleType("simple_ocio"); ocio.ToneMapper = object
+roma = types.ModuleType("roma")  # renderformer/utils/transform.py:3 imports it; nothing of it is called here
+for name, mod in (("h5py", h5py), ("imageio", imageio), ("natsort", natsort), ("simple_ocio", ocio), ("roma", roma)):
+    sys.modules[name] = mod
+sys.path.insert(0, %(ref)r)
+import batch_infer                                                   # the reference's CLI module, unmodified
+ds = batch_infer.TriangleRenderH5Dataset(sys.argv[1], int(sys.argv[2]) if sys.argv[2] != "none" else None)
+item = ds[0]
+np.savez(sys.argv[3], **{k: v.numpy() for k, v in item.items() if hasattr(v, "numpy")})
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "scene_processor")), reason="the reference only exists in the build container")
+@pytest.mark.parametrize("pad", [None, 48])
+def test_scene_loading_and_padding_equal_the_reference_dataset(tmp_path, pad):
+    """batch_infer.py:17-58 (`TriangleRenderH5Dataset.__getitem__`, incl. `--padding_length`) run live on a scene file
+    vs `scene_io.load_scene_file` + `to_pipeline_inputs(pad_to=...)`: the same tensors reach the pipeline."""
+    import torch
+    from renderformer_b200 import scene_io as sio
+    from renderformer_b200.synth import make_scene
+    sc = make_scene(37, 2, seed=12)
+    folder = tmp_path / "scenes"
+    folder.mkdir()
+    stored = {"triangles": sc["triangles"][0].numpy(), "vn": sc["vn"][0].numpy(), "texture": sc["texture"][0].numpy().astype(np.float16),
+              "c2w": sc["c2w"][0].numpy(), "fov": sc["fov"][0, :, 0].numpy()}
+    with open(folder / "a.h5", "wb") as f:  # the stand-in h5py.File of the worker reads an .npz under the .h5 name
+        np.savez(f, **stored)
+    out = str(tmp_path / "item.npz")
+    r = subprocess.run([sys.executable, "-c", DATASET_WORKER % {"ref": REF}, str(folder), "none" if pad is None else str(pad), out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = np.load(out)
+    # ours: the same file through the loader (h5py stand-in = np.load) and the padding of to_pipeline_inputs
+    ours = sio.to_pipeline_inputs({k: (v.astype(np.float32) if v.dtype != bool else v) for k, v in stored.items()}, pad_to=pad)
+    for k in ("triangles", "texture", "vn", "c2w"):
+        assert np.array_equal(ref[k], ours[k][0].numpy()), k
+    assert np.array_equal(ref["mask"], ours["mask"][0].numpy())
+    assert np.array_equal(ref["fov"], ours["fov"][0, :, 0].numpy())       # batch_infer.py:131 adds the trailing axis itself
+    assert ours["triangles"].dtype == torch.float32 and ours["mask"].dtype == torch.bool
