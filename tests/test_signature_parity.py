@@ -156,3 +156,39 @@ def test_config_fields_and_defaults_match_the_reference():
     ours = [[f.name, repr(getattr(RenderFormerConfig(), f.name))] for f in dataclasses.fields(RenderFormerConfig)]
     assert [n for n, _ in ours] == [n for n, _ in ref]
     assert ours == ref
+
+
+@pytest.mark.skipif(not _reference_present(), reason="no reference here (baseline/_ref and /root/reference absent)")
+def test_swin_window_maps_equal_the_reference_functions_live():
+    """The index maps the swin kernel runs on (window-major permutation + region ids, `engine.swin_window_maps`) against
+    the reference's own roll + `window_partition` and `get_swin_attn_mask` (layers/attention.py:205-271,334-339), run
+    live for every grid the released model sees (256^2 ... 1024^2 -> 32^2 ... 128^2 tokens) and a non-square one."""
+    grids = [(8, 8), (16, 24), (32, 32), (64, 64), (128, 128)]
+    worker = ("import sys, json, torch\nsys.path.insert(0, %r)\nfrom oracle.reference_loader import load_reference\n"
+              "load_reference('sdpa')\n"
+              "from renderformer.layers.attention import window_partition, get_swin_attn_mask\n"
+              "out = {}\n"
+              "for H, W in %r:\n"
+              "    for shift in (0, 4):\n"
+              "        tok = torch.arange(H * W, dtype=torch.float32).view(1, H, W, 1)\n"
+              "        g = torch.roll(tok, shifts=(-shift, -shift), dims=(1, 2)) if shift else tok\n"
+              "        perm = window_partition(g, 8).reshape(-1).long()\n"
+              "        key = f'{H}x{W}s{shift}'\n"
+              "        torch.save({'perm': perm, 'mask': get_swin_attn_mask(H, W, 8, shift, 'cpu') if shift else None}, sys.argv[1] + key + '.pt')\n"
+              "print('SWIN_OK')\n" % (ROOT, grids))
+    import tempfile
+    import torch
+    from renderformer_b200.engine import swin_window_maps
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([sys.executable, "-c", worker, d + os.sep], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode == 0 and "SWIN_OK" in r.stdout, r.stderr[-2000:]
+        for H, W in grids:
+            for shift in (0, 4):
+                ref = torch.load(os.path.join(d, f"{H}x{W}s{shift}.pt"))
+                perm, region = swin_window_maps(H, W, shift)
+                assert torch.equal(perm.long(), ref["perm"]), (H, W, shift)
+                if shift:
+                    rg = region.view(-1, 64)
+                    assert torch.equal(rg[:, None, :] == rg[:, :, None], ref["mask"]), (H, W, shift)
+                else:
+                    assert int(region.max()) == 0
