@@ -95,10 +95,18 @@ def main(argv=None, _pipeline=None) -> int:
     dt = time.time() - t0
     print(f"[rank {os.environ.get('RANK', '0')}] {len(paths)} frames of {len(files)} scenes -> {out_dir} in {dt:.2f} s "
           f"({len(paths) / dt:.1f} frames/s incl. file encoding)")
-    if world > 1:
+    if world > 1 and _pipeline is None:
+        # tear-down as in bench.py: CUDA graphs that captured NCCL kernels must be gone before the communicator is, and
+        # the communicator's destructor paths are skipped altogether (destroy_process_group hung a run for minutes)
         import torch.distributed as dist
+        pipe._graphs.clear()
+        pipe._static_states.clear()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
